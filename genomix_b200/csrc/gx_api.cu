@@ -1,0 +1,725 @@
+// gx_api.cu -- context, memory management and the C ABI of libgenomix_gb (include/genomix_gb.h).
+//
+// Host-side shape of one job (single GPU):
+//   gx_push_lines*  : per chunk   line index -> parse -> [grow table] -> extract+insert   (K1+K2)
+//   gx_finish       : heads -> slots, per-slot grouping/sort, size scan, serialise         (K3)
+//   gx_next_*       : stream the record bytes / Hyracks frames back to the caller
+// which replaces the six-operator Hyracks job of JobGenBuildBrujinGraph.assignJob
+// (genomix-hyracks/.../graph/job/JobGenBuildBrujinGraph.java:79-90).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/genomix_gb.h"
+#include "gx_engine.cuh"
+
+using namespace gx;
+
+namespace gx {
+const EngineOps* engine_ops(int kw) {
+    switch (kw) {
+        case 1: return engine_ops_kw1();
+        case 2: return engine_ops_kw2();
+        case 3: return engine_ops_kw3();
+        case 4: return engine_ops_kw4();
+    }
+    return nullptr;
+}
+}  // namespace gx
+
+namespace {
+
+constexpr double GROW_LOAD = 0.70;    // never let distinct + incoming exceed this fraction of capacity
+constexpr double TARGET_LOAD = 0.50;  // capacity chosen for this load
+constexpr u64 MIN_CAPACITY = 1ull << 16;
+constexpr size_t DEFAULT_CHUNK = 64ull << 20;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+enum Phase { PH_PARSE = 0, PH_INSERT = 1, PH_EXCHANGE = 2, PH_FINISH = 3, PH_H2D = 4, PH_COUNT = 8 };
+
+struct PendingTimer {
+    int phase;
+    cudaEvent_t a, b;
+};
+
+}  // namespace
+
+struct gx_ctx {
+    gx_config cfg{};
+    int k = 0, kw = 0;
+    const EngineOps* ops = nullptr;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int sticky = 0;
+
+    Counters* d_ctr = nullptr;
+    Counters* h_ctr = nullptr;  // pinned
+
+    u64* table = nullptr;
+    u64 capacity = 0;
+    u64 grows = 0;
+
+    DevBuf heads, store;
+    DevBuf text, nl_pos, desc, tile_sums;
+    DevBuf hslot, hcount, hstart, hperm, tile_bytes, tile_nodes, records, rec_offsets, parts;
+
+    u64 global_lines = 0;
+    u64 n_nodes = 0, record_bytes = 0;
+    bool finished = false;
+    size_t chunk_bytes = DEFAULT_CHUNK;
+
+    // host slab cache for gx_next_frame
+    std::vector<uint8_t> slab;
+    u64 slab_off = 0, slab_len = 0;
+    u64 frame_byte_cursor = 0, frame_rec_cursor = 0;
+
+    float phase_ms[PH_COUNT] = {0};
+    std::vector<PendingTimer> timers;
+    std::vector<cudaEvent_t> event_pool;
+    u64 launches = 0;
+};
+
+namespace {
+
+thread_local std::string g_create_error;
+
+int fail(gx_ctx* c, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(c, expr)                                                                          \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(c, e__ == cudaErrorMemoryAllocation ? GX_ERR_NOMEM : GX_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, \
+                        cudaGetErrorString(e__), __FILE__, __LINE__);                              \
+    } while (0)
+
+#define GX_TRY(expr)            \
+    do {                        \
+        int r__ = (expr);       \
+        if (r__ != GX_OK) return r__; \
+    } while (0)
+
+// grow-only device buffer; keep_bytes of old content survive a reallocation
+int ensure(gx_ctx* c, DevBuf& b, size_t bytes, size_t keep_bytes = 0, bool zero_new = false) {
+    if (bytes <= b.cap) return GX_OK;
+    size_t ncap = std::max(bytes, b.cap + b.cap / 2);
+    ncap = (ncap + 255) & ~(size_t)255;
+    void* np = nullptr;
+    CUDA_TRY(c, cudaMalloc(&np, ncap + 64));  // +64: kernels may read whole aligned words past the end
+    if (keep_bytes) CUDA_TRY(c, cudaMemcpyAsync(np, b.p, keep_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    if (zero_new) CUDA_TRY(c, cudaMemsetAsync((char*)np + keep_bytes, 0, ncap + 64 - keep_bytes, c->stream));
+    if (b.p) {
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        CUDA_TRY(c, cudaFree(b.p));
+    }
+    b.p = np;
+    b.cap = ncap;
+    return GX_OK;
+}
+
+void release(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+cudaEvent_t get_event(gx_ctx* c) {
+    if (!c->event_pool.empty()) {
+        cudaEvent_t e = c->event_pool.back();
+        c->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct ScopedPhase {
+    gx_ctx* c;
+    PendingTimer t;
+    ScopedPhase(gx_ctx* ctx, int phase) : c(ctx) {
+        t.phase = phase;
+        t.a = get_event(c);
+        t.b = get_event(c);
+        cudaEventRecord(t.a, c->stream);
+    }
+    ~ScopedPhase() {
+        cudaEventRecord(t.b, c->stream);
+        c->timers.push_back(t);
+    }
+};
+
+// resolve finished timers (call after a stream synchronise)
+void drain_timers(gx_ctx* c) {
+    for (auto& t : c->timers) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) c->phase_ms[t.phase] += ms;
+        c->event_pool.push_back(t.a);
+        c->event_pool.push_back(t.b);
+    }
+    c->timers.clear();
+}
+
+int sync_counters(gx_ctx* c) {
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    drain_timers(c);
+    return GX_OK;
+}
+
+int check_launch(gx_ctx* c, const char* what) {
+    ++c->launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(c, GX_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    return GX_OK;
+}
+
+int line_error_to_status(gx_ctx* c, u64 packed) {
+    const u64 line = packed >> 8;
+    const u32 code = (u32)(packed & 0xff);
+    switch (code) {
+        case LE_FORMAT:
+            c->sticky = fail(c, GX_ERR_FORMAT,
+                             "IllegalStateException: input format is not correct! only support id'\\t'readSeq'\\t'mateReadSeq or "
+                             "id'\\t'readSeq' (input line %llu)", (unsigned long long)line);
+            break;
+        case LE_NUMBER:
+            c->sticky = fail(c, GX_ERR_NUMBER, "NumberFormatException: read id is not a long (input line %llu)",
+                             (unsigned long long)line);
+            break;
+        case LE_TOO_SHORT:
+            c->sticky = fail(c, GX_ERR_READ_TOO_SHORT,
+                             "IllegalArgumentException: kmersize (k=%d) is larger than the read length (input line %llu)", c->k,
+                             (unsigned long long)line);
+            break;
+        case LE_READID:
+            c->sticky = fail(c, GX_ERR_READID_RANGE,
+                             "IllegalArgumentException: byte specified for readId will lose some of its bits when saved! "
+                             "(input line %llu)", (unsigned long long)line);
+            break;
+        default:
+            c->sticky = fail(c, GX_ERR_INVALID, "unknown line error %u (input line %llu)", code, (unsigned long long)line);
+    }
+    return c->sticky;
+}
+
+int alloc_table(gx_ctx* c, u64 capacity, u64** out) {
+    void* p = nullptr;
+    const size_t bytes = (size_t)capacity * c->ops->slot_bytes;
+    CUDA_TRY(c, cudaMalloc(&p, bytes));
+    c->ops->init_table((u64*)p, capacity, c->stream);
+    GX_TRY(check_launch(c, "init_table"));
+    *out = (u64*)p;
+    return GX_OK;
+}
+
+// make room for `incoming` more occurrences (upper bound on new distinct keys)
+int reserve_table(gx_ctx* c, u64 distinct, u64 incoming) {
+    const u64 need = distinct + incoming;
+    if (c->table && (double)need <= GROW_LOAD * (double)c->capacity) return GX_OK;
+    u64 ncap = std::max<u64>(MIN_CAPACITY, (u64)((double)need / TARGET_LOAD) + 1);
+    if (c->table) ncap = std::max<u64>(ncap, c->capacity * 2);
+    if (!c->table && c->cfg.expected_kmers)
+        ncap = std::max<u64>(ncap, (u64)((double)c->cfg.expected_kmers / TARGET_LOAD) + 1);
+    u64* nt = nullptr;
+    GX_TRY(alloc_table(c, ncap, &nt));
+    if (c->table) {
+        c->ops->rehash(c->table, c->capacity, nt, ncap, c->stream);
+        GX_TRY(check_launch(c, "rehash"));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        CUDA_TRY(c, cudaFree(c->table));
+        ++c->grows;
+    }
+    c->table = nt;
+    c->capacity = ncap;
+    return GX_OK;
+}
+
+// One chunk of text resident in device memory: line index -> parse -> reserve -> extract+insert.
+int push_chunk_device(gx_ctx* c, const uint8_t* d_text, size_t n) {
+    if (n == 0) return GX_OK;
+    if (n >= (1ull << 32) - 64) return fail(c, GX_ERR_INVALID, "chunk of %zu bytes exceeds the 4 GiB chunk limit", n);
+    const u64 n_tiles = (n + LI_TILE - 1) / LI_TILE;
+    u64 total_nl = 0;
+    {
+        ScopedPhase ph(c, PH_PARSE);
+        GX_TRY(ensure(c, c->tile_sums, (n_tiles + 1) * sizeof(u64)));
+        count_newlines_kernel<<<(unsigned)n_tiles, LI_THREADS, 0, c->stream>>>(d_text, n, (u64*)c->tile_sums.p);
+        GX_TRY(check_launch(c, "count_newlines"));
+        scan_tile_sums_kernel<<<1, 1024, 0, c->stream>>>((u64*)c->tile_sums.p, n_tiles, &c->d_ctr->scratch[0]);
+        GX_TRY(check_launch(c, "scan_tile_sums"));
+    }
+    GX_TRY(sync_counters(c));
+    total_nl = c->h_ctr->scratch[0];
+    const u64 max_lines = total_nl + 1;
+    {
+        ScopedPhase ph(c, PH_PARSE);
+        GX_TRY(ensure(c, c->nl_pos, (max_lines + 1) * sizeof(u32)));
+        GX_TRY(ensure(c, c->desc, max_lines * sizeof(LineDesc)));
+        write_newlines_kernel<<<(unsigned)n_tiles, LI_THREADS, 0, c->stream>>>(d_text, n, (const u64*)c->tile_sums.p,
+                                                                                (u32*)c->nl_pos.p);
+        GX_TRY(check_launch(c, "write_newlines"));
+        finish_line_index_kernel<<<1, 1, 0, c->stream>>>(d_text, n, &c->d_ctr->scratch[0], (u32*)c->nl_pos.p, c->d_ctr);
+        GX_TRY(check_launch(c, "finish_line_index"));
+        parse_lines_kernel<<<(unsigned)((max_lines + PL_THREADS - 1) / PL_THREADS), PL_THREADS, 0, c->stream>>>(
+            d_text, (const u32*)c->nl_pos.p, c->global_lines, c->k, (LineDesc*)c->desc.p, c->d_ctr);
+        GX_TRY(check_launch(c, "parse_lines"));
+    }
+    GX_TRY(sync_counters(c));
+    const Counters& h = *c->h_ctr;
+    const u64 n_lines = h.chunk_lines;
+    c->global_lines += n_lines;
+    if (h.error != ~0ull) return line_error_to_status(c, h.error);
+    if (h.chunk_reads == 0) return GX_OK;
+    // room for this chunk's heads, packed reads and k-mers
+    GX_TRY(ensure(c, c->heads, (size_t)h.head_cursor * c->ops->head_bytes,
+                  (size_t)(h.head_cursor - h.chunk_reads) * c->ops->head_bytes, true));
+    GX_TRY(ensure(c, c->store, (size_t)h.store_cursor, (size_t)(h.store_cursor - h.chunk_store)));
+    GX_TRY(reserve_table(c, h.distinct, h.chunk_occ));
+    {
+        ScopedPhase ph(c, PH_INSERT);
+        ExtractArgs a{};
+        a.text = d_text; a.n_text = n;
+        a.desc = (const LineDesc*)c->desc.p; a.n_lines = n_lines;
+        a.k = c->k;
+        a.table = c->table; a.capacity = c->capacity;
+        a.heads = c->heads.p;
+        a.store = (uint8_t*)c->store.p;
+        a.ctr = c->d_ctr;
+        a.n_ranks = 1; a.rank = 0;
+        c->ops->extract_insert(a, c->stream);
+        GX_TRY(check_launch(c, "extract_insert"));
+    }
+    return GX_OK;
+}
+
+int require_live(gx_ctx* c) {
+    if (!c) return GX_ERR_INVALID;
+    if (c->sticky) return c->sticky;
+    return GX_OK;
+}
+
+// single-thread binary search: largest index i in [lo, n] with offsets[i] <= limit
+__global__ void upper_bound_kernel(const u64* __restrict__ offsets, u64 lo, u64 n, u64 limit, u64* __restrict__ out) {
+    u64 a = lo, b = n;  // invariant offsets[a] <= limit
+    while (a < b) {
+        const u64 mid = a + (b - a + 1) / 2;
+        if (offsets[mid] <= limit) a = mid; else b = mid - 1;
+    }
+    out[0] = a;
+    out[1] = offsets[a];
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int gx_abi_version(void) { return GX_ABI_VERSION; }
+
+const char* gx_last_error(const gx_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int gx_create(const gx_config* cfg, gx_ctx** out) {
+    if (!cfg || !out) return fail(nullptr, GX_ERR_INVALID, "gx_create: null argument");
+    *out = nullptr;
+    if (cfg->abi_version != GX_ABI_VERSION)
+        return fail(nullptr, GX_ERR_INVALID, "gx_create: abi_version %d != %d", cfg->abi_version, GX_ABI_VERSION);
+    if (cfg->kmer_length < 1 || cfg->kmer_length > 32 * GX_MAX_KW)
+        return fail(nullptr, GX_ERR_INVALID, "gx_create: kmer_length %d outside [1, %d]", cfg->kmer_length, 32 * GX_MAX_KW);
+    if (cfg->n_ranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->n_ranks)
+        return fail(nullptr, GX_ERR_INVALID, "gx_create: bad rank %d of %d", cfg->rank, cfg->n_ranks);
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(nullptr, GX_ERR_CUDA, "gx_create: no usable CUDA device (%s); this library has no CPU path",
+                    cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= n_dev)
+        return fail(nullptr, GX_ERR_INVALID, "gx_create: device %d of %d", cfg->device, n_dev);
+    if ((e = cudaSetDevice(cfg->device)) != cudaSuccess)
+        return fail(nullptr, GX_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, cfg->device);
+    if (prop.major != 10)
+        return fail(nullptr, GX_ERR_CUDA, "gx_create: device %d is sm_%d%d; this library ships sm_100a code only", cfg->device,
+                    prop.major, prop.minor);
+    gx_ctx* c = new gx_ctx();
+    c->cfg = *cfg;
+    c->k = cfg->kmer_length;
+    c->kw = (c->k + 31) / 32;
+    c->ops = engine_ops(c->kw);
+    if (cfg->reserved[0]) c->chunk_bytes = (size_t)cfg->reserved[0];
+    auto bail = [&](int code) { g_create_error = c->err; gx_destroy(c); return code; };
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(c, GX_ERR_CUDA, "stream"));
+    c->own_stream = true;
+    if (cudaMalloc((void**)&c->d_ctr, sizeof(Counters)) != cudaSuccess) return bail(fail(c, GX_ERR_NOMEM, "counters"));
+    if (cudaMallocHost((void**)&c->h_ctr, sizeof(Counters)) != cudaSuccess) return bail(fail(c, GX_ERR_NOMEM, "pinned counters"));
+    if (c->ops->prepare() != 0) return bail(fail(c, GX_ERR_CUDA, "cudaFuncSetAttribute failed"));
+    int r = gx_reset(c);
+    if (r != GX_OK) return bail(r);
+    *out = c;
+    return GX_OK;
+}
+
+int gx_reset(gx_ctx* c) {
+    if (!c) return GX_ERR_INVALID;
+    cudaSetDevice(c->cfg.device);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    drain_timers(c);
+    Counters z;
+    memset(&z, 0, sizeof z);
+    z.error = ~0ull;
+    *c->h_ctr = z;
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_ctr, c->h_ctr, sizeof z, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->table) { cudaFree(c->table); c->table = nullptr; c->capacity = 0; }
+    if (c->heads.p) CUDA_TRY(c, cudaMemsetAsync(c->heads.p, 0, c->heads.cap, c->stream));
+    c->grows = 0;
+    c->global_lines = 0;
+    c->n_nodes = c->record_bytes = 0;
+    c->finished = false;
+    c->sticky = 0;
+    c->err.clear();
+    c->slab_len = c->slab_off = 0;
+    c->frame_byte_cursor = c->frame_rec_cursor = 0;
+    memset(c->phase_ms, 0, sizeof c->phase_ms);
+    return GX_OK;
+}
+
+void gx_destroy(gx_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    drain_timers(c);
+    for (auto e : c->event_pool) cudaEventDestroy(e);
+    DevBuf* bufs[] = {&c->heads, &c->store, &c->text, &c->nl_pos, &c->desc, &c->tile_sums, &c->hslot, &c->hcount, &c->hstart,
+                      &c->hperm, &c->tile_bytes, &c->tile_nodes, &c->records, &c->rec_offsets, &c->parts};
+    for (auto* b : bufs) release(*b);
+    if (c->table) cudaFree(c->table);
+    if (c->d_ctr) cudaFree(c->d_ctr);
+    if (c->h_ctr) cudaFreeHost(c->h_ctr);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int gx_set_stream(gx_ctx* c, void* cuda_stream) {
+    if (!c) return GX_ERR_INVALID;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    drain_timers(c);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    c->stream = (cudaStream_t)cuda_stream;
+    c->own_stream = false;
+    return GX_OK;
+}
+
+int gx_push_lines_device(gx_ctx* c, const uint8_t* dev_text, size_t n_bytes) {
+    GX_TRY(require_live(c));
+    if (c->finished) return fail(c, GX_ERR_STATE, "gx_push_lines_device after gx_finish (call gx_reset first)");
+    if (!dev_text && n_bytes) return fail(c, GX_ERR_INVALID, "null text");
+    cudaSetDevice(c->cfg.device);
+    // whole lines per chunk: the split points come from the device (last '\n' before the limit)
+    size_t pos = 0;
+    while (pos < n_bytes) {
+        size_t len = std::min(c->chunk_bytes, n_bytes - pos);
+        if (pos + len < n_bytes) {
+            // back up to the last newline inside the window (copy the window tail to the host: at most 64 KiB at a time)
+            size_t scan_end = pos + len;
+            bool found = false;
+            std::vector<uint8_t> tail(65536);
+            while (scan_end > pos && !found) {
+                const size_t w = std::min<size_t>(tail.size(), scan_end - pos);
+                CUDA_TRY(c, cudaMemcpyAsync(tail.data(), dev_text + scan_end - w, w, cudaMemcpyDeviceToHost, c->stream));
+                CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+                for (size_t i = w; i-- > 0;)
+                    if (tail[i] == '\n') { len = scan_end - w + i + 1 - pos; found = true; break; }
+                scan_end -= w;
+            }
+            if (!found) {  // one line longer than the chunk: extend to its end
+                len = std::min(c->chunk_bytes * 4, n_bytes - pos);
+                if (pos + len < n_bytes) return fail(c, GX_ERR_INVALID, "a single input line exceeds %zu bytes", c->chunk_bytes * 4);
+            }
+        }
+        GX_TRY(push_chunk_device(c, dev_text + pos, len));
+        pos += len;
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    drain_timers(c);
+    return GX_OK;
+}
+
+int gx_push_lines(gx_ctx* c, const uint8_t* host_text, size_t n_bytes) {
+    GX_TRY(require_live(c));
+    if (c->finished) return fail(c, GX_ERR_STATE, "gx_push_lines after gx_finish (call gx_reset first)");
+    if (!host_text && n_bytes) return fail(c, GX_ERR_INVALID, "null text");
+    cudaSetDevice(c->cfg.device);
+    size_t pos = 0;
+    while (pos < n_bytes) {
+        size_t len = std::min(c->chunk_bytes, n_bytes - pos);
+        if (pos + len < n_bytes) {
+            const void* nl = memrchr(host_text + pos, '\n', len);
+            if (nl) len = (const uint8_t*)nl - (host_text + pos) + 1;
+            else {
+                const void* fwd = memchr(host_text + pos + len, '\n', n_bytes - pos - len);
+                len = fwd ? (size_t)((const uint8_t*)fwd - (host_text + pos) + 1) : n_bytes - pos;
+            }
+        }
+        // the previous chunk's kernels still read c->text: the stream orders the copy after them
+        GX_TRY(ensure(c, c->text, len));
+        {
+            ScopedPhase ph(c, PH_H2D);
+            CUDA_TRY(c, cudaMemcpyAsync(c->text.p, host_text + pos, len, cudaMemcpyHostToDevice, c->stream));
+        }
+        GX_TRY(push_chunk_device(c, (const uint8_t*)c->text.p, len));
+        pos += len;
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    drain_timers(c);
+    return GX_OK;
+}
+
+int gx_push_fastq(gx_ctx* c, const uint8_t*, size_t, const uint8_t*, size_t, uint64_t) {
+    GX_TRY(require_live(c));
+    return fail(c, GX_ERR_STATE, "gx_push_fastq: not implemented in this build");
+}
+
+int gx_finish(gx_ctx* c) {
+    GX_TRY(require_live(c));
+    if (c->finished) return GX_OK;
+    cudaSetDevice(c->cfg.device);
+    GX_TRY(sync_counters(c));
+    if (c->h_ctr->error != ~0ull) return line_error_to_status(c, c->h_ctr->error);
+    if (!c->table) GX_TRY(reserve_table(c, 0, 0));  // empty job: empty table, zero records
+    const u64 cap = c->capacity;
+    const u64 n_heads = c->h_ctr->head_cursor;
+    const u64 n_tiles = (cap + EM_THREADS - 1) / EM_THREADS;
+    {
+        ScopedPhase ph(c, PH_FINISH);
+        if (n_heads) {
+            if (n_heads >= 0xffffffffull) return fail(c, GX_ERR_INVALID, "more than 2^32-1 read heads on one rank");
+            const u64 s_tiles = (cap + TS_TILE - 1) / TS_TILE;
+            GX_TRY(ensure(c, c->hslot, n_heads * sizeof(u64)));
+            GX_TRY(ensure(c, c->hcount, cap * sizeof(u32)));
+            GX_TRY(ensure(c, c->hstart, (cap + 1) * sizeof(u32)));
+            GX_TRY(ensure(c, c->hperm, n_heads * sizeof(u32)));
+            GX_TRY(ensure(c, c->tile_sums, (s_tiles + 1) * sizeof(u64)));
+            CUDA_TRY(c, cudaMemsetAsync(c->hcount.p, 0, cap * sizeof(u32), c->stream));
+            CUDA_TRY(c, cudaMemsetAsync(c->hperm.p, 0xff, n_heads * sizeof(u32), c->stream));
+            c->ops->heads_count(c->heads.p, n_heads, c->table, cap, (u64*)c->hslot.p, (u32*)c->hcount.p, c->d_ctr, c->stream);
+            GX_TRY(check_launch(c, "heads_count"));
+            tile_sum_u32_kernel<<<(unsigned)s_tiles, TS_THREADS, 0, c->stream>>>((const u32*)c->hcount.p, cap, (u64*)c->tile_sums.p);
+            GX_TRY(check_launch(c, "tile_sum_u32"));
+            scan_tile_sums_kernel<<<1, 1024, 0, c->stream>>>((u64*)c->tile_sums.p, s_tiles, &c->d_ctr->scratch[0]);
+            GX_TRY(check_launch(c, "scan_tile_sums"));
+            tile_scan_u32_kernel<<<(unsigned)s_tiles, TS_THREADS, 0, c->stream>>>((const u32*)c->hcount.p, cap,
+                                                                                  (const u64*)c->tile_sums.p, (u32*)c->hstart.p);
+            GX_TRY(check_launch(c, "tile_scan_u32"));
+            CUDA_TRY(c, cudaMemsetAsync(c->hcount.p, 0, cap * sizeof(u32), c->stream));
+            heads_scatter_kernel<<<(unsigned)((n_heads + 255) / 256), 256, 0, c->stream>>>(
+                (const u64*)c->hslot.p, n_heads, cap, (const u32*)c->hstart.p, (u32*)c->hcount.p, (u32*)c->hperm.p);
+            GX_TRY(check_launch(c, "heads_scatter"));
+            c->ops->heads_sort(c->heads.p, (const u64*)c->hslot.p, n_heads, cap, (const u32*)c->hstart.p, (u32*)c->hcount.p,
+                               (u32*)c->hperm.p, c->d_ctr, c->stream);
+            GX_TRY(check_launch(c, "heads_sort"));
+        }
+        GX_TRY(ensure(c, c->tile_bytes, (n_tiles + 1) * sizeof(u64)));
+        GX_TRY(ensure(c, c->tile_nodes, (n_tiles + 1) * sizeof(u64)));
+    }
+    EmitArgs a{};
+    a.table = c->table; a.capacity = cap; a.k = c->k;
+    a.heads = c->heads.p;
+    a.hstart = n_heads ? (const u32*)c->hstart.p : nullptr;
+    a.hcount = n_heads ? (const u32*)c->hcount.p : nullptr;
+    a.hperm = n_heads ? (const u32*)c->hperm.p : nullptr;
+    a.store = (const uint8_t*)c->store.p;
+    a.tile_bytes = (u64*)c->tile_bytes.p; a.tile_nodes = (u64*)c->tile_nodes.p;
+    {
+        ScopedPhase ph(c, PH_FINISH);
+        c->ops->emit_size(a, c->stream);
+        GX_TRY(check_launch(c, "emit_size"));
+        scan_tile_sums_kernel<<<1, 1024, 0, c->stream>>>((u64*)c->tile_bytes.p, n_tiles, &c->d_ctr->scratch[0]);
+        GX_TRY(check_launch(c, "scan_tile_sums"));
+        scan_tile_sums_kernel<<<1, 1024, 0, c->stream>>>((u64*)c->tile_nodes.p, n_tiles, &c->d_ctr->scratch[1]);
+        GX_TRY(check_launch(c, "scan_tile_sums"));
+    }
+    GX_TRY(sync_counters(c));
+    if (c->h_ctr->table_overflow)
+        return c->sticky = fail(c, GX_ERR_NOMEM, "internal error: %llu k-mer inserts ran out of probe budget (table full?)",
+                                (unsigned long long)c->h_ctr->table_overflow);
+    if (c->h_ctr->heads_missing)
+        return c->sticky = fail(c, GX_ERR_INVALID, "internal error: %llu read heads without a node",
+                                (unsigned long long)c->h_ctr->heads_missing);
+    c->record_bytes = c->h_ctr->scratch[0];
+    c->n_nodes = c->h_ctr->scratch[1];
+    GX_TRY(ensure(c, c->records, (size_t)c->record_bytes + 16));
+    GX_TRY(ensure(c, c->rec_offsets, (size_t)(c->n_nodes + 1) * sizeof(u64)));
+    a.out = (uint8_t*)c->records.p;
+    a.rec_offsets = (u64*)c->rec_offsets.p;
+    {
+        ScopedPhase ph(c, PH_FINISH);
+        c->ops->emit_serialise(a, c->stream);
+        GX_TRY(check_launch(c, "emit_serialise"));
+        CUDA_TRY(c, cudaMemcpyAsync((u64*)c->rec_offsets.p + c->n_nodes, &c->h_ctr->scratch[0], sizeof(u64),
+                                    cudaMemcpyHostToDevice, c->stream));
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    drain_timers(c);
+    c->finished = true;
+    return GX_OK;
+}
+
+int64_t gx_num_nodes(gx_ctx* c) { return (c && c->finished) ? (int64_t)c->n_nodes : -1; }
+int64_t gx_record_bytes(gx_ctx* c) { return (c && c->finished) ? (int64_t)c->record_bytes : -1; }
+
+int gx_records_device(gx_ctx* c, const uint8_t** dev_records, const uint64_t** dev_offsets) {
+    GX_TRY(require_live(c));
+    if (!c->finished) return fail(c, GX_ERR_STATE, "gx_records_device before gx_finish");
+    if (dev_records) *dev_records = (const uint8_t*)c->records.p;
+    if (dev_offsets) *dev_offsets = (const uint64_t*)c->rec_offsets.p;
+    return GX_OK;
+}
+
+int gx_next_records(gx_ctx* c, uint64_t* cursor, uint8_t* host_buf, size_t cap, size_t* used) {
+    GX_TRY(require_live(c));
+    if (!c->finished) return fail(c, GX_ERR_STATE, "gx_next_records before gx_finish");
+    if (!cursor || !used || (!host_buf && cap)) return fail(c, GX_ERR_INVALID, "null argument");
+    cudaSetDevice(c->cfg.device);
+    *used = 0;
+    if (*cursor >= c->record_bytes) return GX_OK;
+    u64 end = c->record_bytes;
+    if (end - *cursor > cap) {
+        // largest record boundary <= cursor + cap
+        upper_bound_kernel<<<1, 1, 0, c->stream>>>((const u64*)c->rec_offsets.p, 0, c->n_nodes, *cursor + cap,
+                                                   &c->d_ctr->scratch[0]);
+        GX_TRY(check_launch(c, "upper_bound"));
+        GX_TRY(sync_counters(c));
+        end = c->h_ctr->scratch[1];
+        if (end <= *cursor) return fail(c, GX_ERR_BUFFER, "buffer of %zu bytes cannot hold the next record", cap);
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(host_buf, (const uint8_t*)c->records.p + *cursor, end - *cursor, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    *used = (size_t)(end - *cursor);
+    *cursor = end;
+    return GX_OK;
+}
+
+int gx_next_frame(gx_ctx* c, uint64_t* cursor, uint8_t* frame, int32_t frame_size, int32_t* n_tuples) {
+    GX_TRY(require_live(c));
+    if (!c->finished) return fail(c, GX_ERR_STATE, "gx_next_frame before gx_finish");
+    if (!cursor || !frame || !n_tuples || frame_size < 16) return fail(c, GX_ERR_INVALID, "bad argument");
+    cudaSetDevice(c->cfg.device);
+    *n_tuples = 0;
+    if (*cursor == 0) { c->frame_byte_cursor = 0; c->frame_rec_cursor = 0; c->slab_len = 0; }
+    if (*cursor != c->frame_rec_cursor) return fail(c, GX_ERR_INVALID, "gx_next_frame: frames must be pulled in order");
+    const u32 nb = (u32)(c->k + 3) / 4;
+    int32_t data_end = 0, count = 0;
+    auto be32 = [](const uint8_t* p) { return ((u32)p[0] << 24) | ((u32)p[1] << 16) | ((u32)p[2] << 8) | (u32)p[3]; };
+    auto put32 = [](uint8_t* p, u32 v) { p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v; };
+    while (c->frame_byte_cursor < c->record_bytes) {
+        // make sure the next record is in the host slab
+        auto in_slab = [&](u64 off, u64 len) { return off >= c->slab_off && off + len <= c->slab_off + c->slab_len; };
+        if (!in_slab(c->frame_byte_cursor, 8) ||
+            !in_slab(c->frame_byte_cursor, 8 + be32(&c->slab[c->frame_byte_cursor - c->slab_off]))) {
+            u64 want = std::max<u64>(8ull << 20, 2 * (u64)frame_size);
+            if (in_slab(c->frame_byte_cursor, 8))
+                want = std::max<u64>(want, 8 + (u64)be32(&c->slab[c->frame_byte_cursor - c->slab_off]));
+            want = std::min<u64>(want, c->record_bytes - c->frame_byte_cursor);
+            c->slab.resize(want);
+            CUDA_TRY(c, cudaMemcpyAsync(c->slab.data(), (const uint8_t*)c->records.p + c->frame_byte_cursor, want,
+                                        cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+            c->slab_off = c->frame_byte_cursor;
+            c->slab_len = want;
+        }
+        const uint8_t* r = &c->slab[c->frame_byte_cursor - c->slab_off];
+        const u32 rec_len = be32(r);
+        const u32 node_len = rec_len - (4 + nb);
+        const int32_t tuple_len = 8 + (int32_t)nb + (int32_t)node_len;
+        // FrameTupleAppender.append (FrameTupleAppender.java:57-70)
+        if ((int64_t)data_end + tuple_len + 4 + (int64_t)(count + 1) * 4 > frame_size) {
+            if (count == 0)
+                return fail(c, GX_ERR_BUFFER, "Failed to copy an record into a frame: the record kmerByteSize is too large.");
+            break;
+        }
+        uint8_t* t = frame + data_end;
+        put32(t, nb);
+        put32(t + 4, nb + node_len);
+        memcpy(t + 8, r + 12, nb);                   // Kmer field: bytes without the VKmer length header
+        memcpy(t + 8 + nb, r + 12 + nb, node_len);   // Node field
+        data_end += tuple_len;
+        ++count;
+        put32(frame + frame_size - 4 - 4 * count, (u32)data_end);
+        c->frame_byte_cursor += 8 + rec_len;
+        ++c->frame_rec_cursor;
+    }
+    put32(frame + frame_size - 4, (u32)count);
+    *n_tuples = count;
+    *cursor = c->frame_rec_cursor;
+    return GX_OK;
+}
+
+int gx_partition_records(gx_ctx* c, int32_t n_parts, int32_t* host_parts) {
+    GX_TRY(require_live(c));
+    if (!c->finished) return fail(c, GX_ERR_STATE, "gx_partition_records before gx_finish");
+    if (n_parts < 1 || !host_parts) return fail(c, GX_ERR_INVALID, "bad argument");
+    if (c->n_nodes == 0) return GX_OK;
+    cudaSetDevice(c->cfg.device);
+    GX_TRY(ensure(c, c->parts, c->n_nodes * sizeof(int)));
+    partition_records_kernel<<<(unsigned)((c->n_nodes + 255) / 256), 256, 0, c->stream>>>(
+        (const uint8_t*)c->records.p, (const u64*)c->rec_offsets.p, c->n_nodes, n_parts, (int*)c->parts.p);
+    GX_TRY(check_launch(c, "partition_records"));
+    CUDA_TRY(c, cudaMemcpyAsync(host_parts, c->parts.p, c->n_nodes * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return GX_OK;
+}
+
+int gx_get_stats(gx_ctx* c, gx_stats* out) {
+    if (!c || !out) return GX_ERR_INVALID;
+    cudaSetDevice(c->cfg.device);
+    GX_TRY(sync_counters(c));
+    memset(out, 0, sizeof *out);
+    out->lines = c->global_lines;
+    out->reads = c->h_ctr->reads;
+    out->bases = c->h_ctr->bases;
+    out->kmer_occurrences = c->h_ctr->occurrences;
+    out->distinct_kmers = c->h_ctr->distinct;
+    out->read_heads = c->h_ctr->read_heads;
+    out->record_bytes = c->record_bytes;
+    out->table_capacity = c->capacity;
+    out->table_grows = c->grows;
+    return GX_OK;
+}
+
+int gx_phase_ms(gx_ctx* c, float out_ms[8]) {
+    if (!c || !out_ms) return GX_ERR_INVALID;
+    cudaSetDevice(c->cfg.device);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    drain_timers(c);
+    for (int i = 0; i < 8; ++i) out_ms[i] = c->phase_ms[i];
+    return GX_OK;
+}
+
+uint64_t gx_kernel_launches(gx_ctx* c) { return c ? c->launches : 0; }
+
+int gx_mg_unique_id(uint8_t*) { return GX_ERR_STATE; }
+int gx_mg_init(gx_ctx* c, const uint8_t*) { return fail(c, GX_ERR_STATE, "multi-GPU exchange not built"); }
+int gx_mg_exchange(gx_ctx* c) { return fail(c, GX_ERR_STATE, "multi-GPU exchange not built"); }
+
+}  // extern "C"

@@ -1,0 +1,593 @@
+// gx_engine.cuh -- the KW-templated kernels of the graph-build path and their launchers.
+//
+//   K1+K2  extract_insert_kernel   read -> canonical k-mers -> hash-table upsert   (single GPU: fused)
+//   K1x    extract_route_kernel    read -> k-mer records bucketed by owner GPU     (multi GPU)
+//   K2x    insert_records_kernel   received records -> upsert
+//   K3     heads_* + emit_*        read-head grouping, sizing, Node serialisation
+//
+// Reference semantics restated by each kernel are cited at the kernel.
+#pragma once
+#include "gx_internal.cuh"
+#include "gx_parse.cuh"
+#include "gx_scan.cuh"
+#include "gx_table.cuh"
+
+namespace gx {
+
+static constexpr int EX_THREADS = 256;
+static constexpr int EX_WARPS = EX_THREADS / 32;
+static constexpr int WIN_BYTES = 512;                       // packed letters per warp window: 2048 letters
+static constexpr int WIN_WORDS = WIN_BYTES / 8 + GX_MAX_KW + 2;
+static constexpr int WIN_POSITIONS = 4 * WIN_BYTES - 160;   // k-mer start positions per window (k <= 128)
+
+struct ExtractArgs {
+    const uint8_t* text; u64 n_text;
+    const LineDesc* desc; u64 n_lines;
+    int k;
+    u64* table; u64 capacity;
+    void* heads;
+    uint8_t* store;
+    Counters* ctr;
+    // routing (multi-GPU) -- unused by the fused kernel
+    u32 n_ranks; u32 rank;
+    u64* route_keys;      // [n_ranks][route_cap][KW]
+    unsigned short* route_meta;  // [n_ranks][route_cap]
+    u64 route_cap;
+    u64* route_count;     // [n_ranks]
+};
+
+// four text bytes at the 4-byte aligned address `w` -> one packed quad; bytes outside [lo, hi) read as 'A'
+__device__ __forceinline__ u32 load_quad(const uint8_t* w, const uint8_t* lo, const uint8_t* hi) {
+    u32 x;
+    if (w >= lo && w + 4 <= hi) {
+        x = __ldg(reinterpret_cast<const u32*>(w));
+    } else {
+        x = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (w + i >= lo && w + i < hi) x |= (u32)__ldg(w + i) << (8 * i);
+    }
+    u32 q = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        bool ok;
+        q |= code_of((x >> (8 * i)) & 0xffu, ok) << (2 * i);
+    }
+    return q;
+}
+
+// letters [a, a+k) of the packed window -> f
+template <int KW>
+__device__ __forceinline__ void window_kmer(const u64* __restrict__ W, u32 a, int k, u64 (&f)[KW]) {
+    const u32 wi = a >> 5;
+    const u32 sh = (a & 31u) * 2u;
+    u64 lo = W[wi];
+#pragma unroll
+    for (int j = 0; j < KW; ++j) {
+        const u64 hi = W[wi + j + 1];
+        f[j] = (lo >> sh) | ((hi << 1) << (63u - sh));
+        lo = hi;
+    }
+    f[KW - 1] &= top_word_mask(k);
+}
+
+__device__ __forceinline__ u32 window_letter(const u64* __restrict__ W, u32 a) {
+    return (u32)(W[a >> 5] >> ((a & 31u) * 2u)) & 3u;
+}
+
+// Pack a read's letters into the read store in VKmer byte order (VKmer.java:462-479: letter i at bits
+// 2*(i%4) of byte nb-1-i/4); non-ACGT letters pack as A (GeneCode.java:29-50). Warp-cooperative.
+__device__ __forceinline__ void pack_read_to_store(const uint8_t* __restrict__ src, u32 len, uint8_t* __restrict__ dst,
+                                                   int lane) {
+    const u32 nb = (len + 3) / 4;
+    for (u32 q = lane; q < nb; q += 32) {
+        u32 b = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const u32 idx = 4 * q + i;
+            if (idx < len) {
+                bool ok;
+                b |= code_of(__ldg(src + idx), ok) << (2 * i);
+            }
+        }
+        dst[nb - 1 - q] = (uint8_t)b;
+    }
+}
+
+// Edge-mask bits of one occurrence, exactly as setEdgesForCurAndNext assigns them
+// (ReadsKeyValueParserFactory.java:209-233) seen from the canonical key (gx_internal.cuh header):
+//   to next  : cur F -> FF/FR with base b;      cur R -> RF/RR with base 3-b
+//   from prev: cur F -> RR/RF with base a;      cur R -> FR/FF with base 3-a
+__device__ __forceinline__ u32 edge_bit_next(bool cur_rev, bool next_rev, u32 b) {
+    const u32 type = cur_rev ? (next_rev ? 3u : 2u) : (next_rev ? 1u : 0u);
+    return 1u << (type * 4u + (cur_rev ? 3u - b : b));
+}
+__device__ __forceinline__ u32 edge_bit_prev(bool cur_rev, bool prev_rev, u32 a) {
+    const u32 type = cur_rev ? (prev_rev ? 0u : 1u) : (prev_rev ? 2u : 3u);
+    return 1u << (type * 4u + (cur_rev ? 3u - a : a));
+}
+
+// K1 (+K2 when ROUTE == false).
+// Restates ReadsKeyValueParserFactory.SplitReads (:150-196): for every position p of every split mate the
+// forward and reverse-complement k-mers, dir = fwd <= rc ? FORWARD : REVERSE, key = the smaller, one
+// tuple (key, Node{coverage 1, <=2 edges, read head on p == 0}). The tuple is never materialised: it is
+// folded straight into the table (ROUTE == false) or appended to its owner GPU's bucket (ROUTE == true).
+// One warp per input line; lanes 1..30 own consecutive positions, lanes 0 and 31 are halo lanes that
+// only compute the direction of the neighbouring position.
+template <int KW, bool ROUTE>
+__global__ void __launch_bounds__(EX_THREADS) extract_kernel(ExtractArgs a) {
+    __shared__ u64 sq[EX_WARPS][WIN_WORDS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64* W = sq[warp];
+    uint8_t* Wb = reinterpret_cast<uint8_t*>(W);
+    Head<KW>* heads = reinterpret_cast<Head<KW>*>(a.heads);
+    const int k = a.k;
+    const uint8_t* text_lo = a.text;
+    const uint8_t* text_hi = a.text + a.n_text;
+    u32 new_slots = 0;
+
+    for (u64 line = (u64)blockIdx.x * EX_WARPS + warp; line < a.n_lines; line += (u64)gridDim.x * EX_WARPS) {
+        const LineDesc d = a.desc[line];
+        if ((d.flags & 3u) == 0) continue;
+#pragma unroll 1
+        for (int mate = 0; mate < 2; ++mate) {
+            const u32 len = d.len[mate];
+            if (len == 0) continue;
+            const uint8_t* rd = a.text + d.off[mate];
+            pack_read_to_store(rd, len, a.store + d.store[mate], lane);
+            if (!(d.flags & (1u << mate))) continue;
+            const u32 npos = len - (u32)k + 1u;
+            for (u32 pa = 0; pa < npos; pa += WIN_POSITIONS) {
+                const u32 pb = min(pa + (u32)WIN_POSITIONS, npos);
+                const u32 lo = pa > 0 ? pa - 1 : 0;
+                const u32 hi = pb < npos ? pb + k : len;
+                const uint8_t* src = rd + lo;
+                const u32 m = (u32)((uintptr_t)src & 3u);
+                const uint8_t* aligned = src - m;
+                const u32 nwords = (m + (hi - lo) + 3u) / 4u;
+                __syncwarp();
+                for (u32 j = lane; j < nwords; j += 32) Wb[j] = (uint8_t)load_quad(aligned + 4 * j, text_lo, text_hi);
+                __syncwarp();
+                for (u32 g = pa; g < pb; g += 30) {
+                    const long long p = (long long)g - 1 + lane;
+                    const bool comp = p >= 0 && p < (long long)npos && p <= (long long)pb;
+                    u64 f[KW], rc[KW];
+                    bool rev = false;
+                    if (comp) {
+                        window_kmer<KW>(W, (u32)(p - lo) + m, k, f);
+                        revcomp_key<KW>(f, k, rc);
+                        rev = !key_le<KW>(f, rc);
+                    }
+                    const u32 dirs = __ballot_sync(0xffffffffu, comp && rev);
+                    const bool active = lane >= 1 && lane <= 30 && p < (long long)pb;
+                    if (active) {
+                        u32 mask = 0;
+                        if (p + 1 < (long long)npos)
+                            mask |= edge_bit_next(rev, (dirs >> (lane + 1)) & 1u, window_letter(W, (u32)(p + k - lo) + m));
+                        if (p > 0)
+                            mask |= edge_bit_prev(rev, (dirs >> (lane - 1)) & 1u, window_letter(W, (u32)(p - 1 - lo) + m));
+                        u64 key[KW];
+#pragma unroll
+                        for (int i = 0; i < KW; ++i) key[i] = rev ? rc[i] : f[i];
+                        if (p == 0) {
+                            Head<KW>& h = heads[d.head_idx[mate]];
+#pragma unroll
+                            for (int i = 0; i < KW; ++i) h.key[i] = key[i];
+                            // offset 0 unflipped, K-1 flipped (:165-170); library always 0 (:98-106)
+                            h.uuid = (rev ? ((u64)(k - 1) << 40) : 0ull) | ((u64)mate << 35) | d.read_id;
+                            h.this_off = d.store[mate];
+                            h.mate_off = d.store[1 - mate];
+                            h.this_len = len;
+                            h.mate_len = d.len[1 - mate];
+                            h.flipped = rev ? 1u : 0u;
+                            h.valid = 1u;
+                        }
+                        if constexpr (!ROUTE) {
+                            bool is_new;
+                            if (table_upsert<KW>(a.table, a.capacity, key, 1ull, mask, is_new) == a.capacity)
+                                atomicAdd(&a.ctr->table_overflow, 1ull);
+                            new_slots += is_new ? 1u : 0u;
+                        } else {
+                            const u32 owner = owner_of(hash_key<KW>(key), a.n_ranks);
+                            const u64 idx = atomicAdd(a.route_count + owner, 1ull);
+                            u64* kd = a.route_keys + ((u64)owner * a.route_cap + idx) * KW;
+#pragma unroll
+                            for (int i = 0; i < KW; ++i) kd[i] = key[i];
+                            a.route_meta[(u64)owner * a.route_cap + idx] = (unsigned short)mask;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if constexpr (!ROUTE) {
+#pragma unroll
+        for (int dlt = 16; dlt > 0; dlt >>= 1) new_slots += __shfl_xor_sync(0xffffffffu, new_slots, dlt);
+        if (lane == 0 && new_slots) atomicAdd(&a.ctr->distinct, (u64)new_slots);
+    }
+}
+
+// K2x: upsert pre-extracted (key, mask, count) records (received from other GPUs, or partial aggregates).
+template <int KW>
+__global__ void __launch_bounds__(256) insert_records_kernel(const u64* __restrict__ keys,
+                                                             const unsigned short* __restrict__ meta,
+                                                             const u32* __restrict__ counts, u64 n, u64* table,
+                                                             u64 capacity, Counters* ctr) {
+    u32 new_slots = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        u64 key[KW];
+#pragma unroll
+        for (int j = 0; j < KW; ++j) key[j] = keys[i * KW + j];
+        bool is_new;
+        if (table_upsert<KW>(table, capacity, key, counts ? (u64)counts[i] : 1ull, meta[i], is_new) == capacity)
+            atomicAdd(&ctr->table_overflow, 1ull);
+        new_slots += is_new ? 1u : 0u;
+    }
+#pragma unroll
+    for (int dlt = 16; dlt > 0; dlt >>= 1) new_slots += __shfl_xor_sync(0xffffffffu, new_slots, dlt);
+    if ((threadIdx.x & 31) == 0 && new_slots) atomicAdd(&ctr->distinct, (u64)new_slots);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int KW>
+__global__ void __launch_bounds__(256) init_table_kernel(u64* __restrict__ table, u64 capacity) {
+    constexpr int SW = SlotTraits<KW>::WORDS;
+    const u64 n = capacity * SW;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const int w = (int)(i % SW);
+        table[i] = (KW <= 2 && w < KW) ? EMPTY_WORD : 0ull;
+    }
+}
+
+// grow: re-insert every occupied slot of the old table (count and mask carried over)
+template <int KW>
+__global__ void __launch_bounds__(256) rehash_kernel(const u64* __restrict__ old_table, u64 old_capacity,
+                                                     u64* __restrict__ table, u64 capacity) {
+    constexpr int SW = SlotTraits<KW>::WORDS;
+    for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < old_capacity; s += (u64)gridDim.x * blockDim.x) {
+        const u64* p = old_table + s * SW;
+        if (!slot_occupied<KW>(p)) continue;
+        u64 key[KW];
+#pragma unroll
+        for (int j = 0; j < KW; ++j) key[j] = p[j];
+        const u64 v = p[KW];
+        bool is_new;
+        table_upsert<KW>(table, capacity, key, v & COUNT_MASK, (u32)(v >> MASK_SHIFT), is_new);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3a: read heads -> owning slot (the reference carries the ReadHeadInfo inside the first k-mer's tuple and
+// unions TreeSets per key, AggregateKmerAggregateFactory.java:120-123,141-143)
+template <int KW>
+__global__ void __launch_bounds__(256) heads_count_kernel(const Head<KW>* __restrict__ heads, u64 n_heads,
+                                                          const u64* __restrict__ table, u64 capacity,
+                                                          u64* __restrict__ hslot, u32* __restrict__ hcount,
+                                                          Counters* ctr) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_heads) return;
+    const Head<KW>& h = heads[i];
+    u64 slot = capacity;
+    if (h.valid) {
+        u64 key[KW];
+#pragma unroll
+        for (int j = 0; j < KW; ++j) key[j] = h.key[j];
+        slot = table_find<KW>(table, capacity, key);
+    }
+    hslot[i] = slot;
+    if (slot == capacity) { atomicAdd(&ctr->heads_missing, 1ull); return; }
+    atomicAdd(hcount + slot, 1u);
+}
+
+static __global__ void __launch_bounds__(256) heads_scatter_kernel(const u64* __restrict__ hslot, u64 n_heads, u64 capacity,
+                                                            const u32* __restrict__ hstart, u32* __restrict__ hfill,
+                                                            u32* __restrict__ hperm) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_heads) return;
+    const u64 slot = hslot[i];
+    if (slot == capacity) return;
+    const u32 pos = hstart[slot] + atomicAdd(hfill + slot, 1u);
+    hperm[pos] = (u32)i;
+}
+
+// order of ReadHeadInfo.compareTo (ReadHeadInfo.java:247-264): offset, library, mate, readId == numeric order of
+// the uuid for the non-negative offsets graph build produces; unflipped set before flipped set; ties (same uuid
+// from two input lines) resolved to the earlier line, which the TreeSet keeps.
+template <int KW>
+__device__ __forceinline__ bool head_less(const Head<KW>* __restrict__ heads, u32 x, u32 y) {
+    const Head<KW>& a = heads[x];
+    const Head<KW>& b = heads[y];
+    if (a.flipped != b.flipped) return a.flipped < b.flipped;
+    if (a.uuid != b.uuid) return a.uuid < b.uuid;
+    return x < y;
+}
+
+template <int KW>
+__global__ void __launch_bounds__(256) heads_sort_kernel(const Head<KW>* __restrict__ heads, const u64* __restrict__ hslot,
+                                                         u64 n_heads, u64 capacity, const u32* __restrict__ hstart,
+                                                         u32* __restrict__ hcount, u32* __restrict__ hperm,
+                                                         Counters* ctr) {
+    const u64 pos = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 kept = 0;
+    if (pos < n_heads) {
+        // hperm is dense over [0, n_found); positions past it are unused
+        const u32 hi = hperm[pos];
+        if (hi != 0xffffffffu) {
+            const u64 slot = hslot[hi];
+            if (slot != capacity && hstart[slot] == (u32)pos) {  // group leader
+                const u32 n = hcount[slot];
+                u32* v = hperm + pos;
+                if (n > 1) {
+                    if (n <= 16) {
+                        for (u32 i = 1; i < n; ++i) {
+                            const u32 x = v[i];
+                            u32 j = i;
+                            while (j > 0 && head_less<KW>(heads, x, v[j - 1])) { v[j] = v[j - 1]; --j; }
+                            v[j] = x;
+                        }
+                    } else {  // heapsort
+                        auto sift = [&](u32 start, u32 end) {
+                            u32 root = start;
+                            for (;;) {
+                                u32 child = 2 * root + 1;
+                                if (child >= end) break;
+                                if (child + 1 < end && head_less<KW>(heads, v[child], v[child + 1])) ++child;
+                                if (head_less<KW>(heads, v[root], v[child])) {
+                                    const u32 t = v[root]; v[root] = v[child]; v[child] = t;
+                                    root = child;
+                                } else break;
+                            }
+                        };
+                        for (u32 s = n / 2; s-- > 0;) sift(s, n);
+                        for (u32 e = n - 1; e > 0; --e) {
+                            const u32 t = v[0]; v[0] = v[e]; v[e] = t;
+                            sift(0, e);
+                        }
+                    }
+                }
+                // TreeSet de-duplication
+                kept = n ? 1u : 0u;
+                for (u32 i = 1; i < n; ++i) {
+                    const Head<KW>& p = heads[v[kept - 1]];
+                    const Head<KW>& c = heads[v[i]];
+                    if (p.flipped == c.flipped && p.uuid == c.uuid) continue;
+                    v[kept++] = v[i];
+                }
+                hcount[slot] = kept;
+            }
+        }
+    }
+    const u64 tot = block_reduce_sum<256>((u64)kept);
+    if (threadIdx.x == 0 && tot) atomicAdd(&ctr->read_heads, tot);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3b: sizes and serialisation of `VKmer key | Node` records.
+static constexpr int EM_THREADS = 1024;               // slots per tile
+static constexpr int EM_STAGE_BYTES = 96 * 1024;      // shared-memory staging of a tile's records
+
+struct EmitArgs {
+    const u64* table; u64 capacity; int k;
+    const void* heads; const u32* hstart; const u32* hcount; const u32* hperm;
+    const uint8_t* store;
+    u64* tile_bytes; u64* tile_nodes;   // per tile: sums (size pass) then exclusive bases (after the scan)
+    uint8_t* out; u64* rec_offsets;
+};
+
+__device__ __forceinline__ u32 head_bytes(u32 this_len, u32 mate_len) {
+    // ReadHeadInfo.write (ReadHeadInfo.java:205-212): flags, long, VKmer this, [VKmer mate]
+    return 1u + 8u + 4u + (this_len + 3u) / 4u + (mate_len ? 4u + (mate_len + 3u) / 4u : 0u);
+}
+
+template <int KW>
+__device__ __forceinline__ u32 node_record_bytes(const EmitArgs& a, u64 slot, u64 val, u32& n_unflipped, u32& n_flipped) {
+    const u32 nb = (u32)(a.k + 3) / 4u;
+    const u32 mask = (u32)(val >> MASK_SHIFT);
+    u32 sz = 8u + 4u + nb + 1u + 4u;  // recLen, keyLen, VKmer key, active byte, coverage float
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const u32 c = __popc((mask >> (4 * t)) & 0xfu);
+        if (c) sz += 4u + c * (4u + nb);
+    }
+    n_unflipped = n_flipped = 0;
+    const u32 n = a.hcount ? a.hcount[slot] : 0u;
+    if (n) {
+        const Head<KW>* heads = reinterpret_cast<const Head<KW>*>(a.heads);
+        const u32* v = a.hperm + a.hstart[slot];
+        for (u32 i = 0; i < n; ++i) {
+            const Head<KW>& h = heads[v[i]];
+            sz += head_bytes(h.this_len, h.mate_len);
+            if (h.flipped) ++n_flipped; else ++n_unflipped;
+        }
+        if (n_unflipped) sz += 5u;  // boolean wholeBody + int size (ExternalableTreeSet.java:236-253)
+        if (n_flipped) sz += 5u;
+    }
+    return sz;
+}
+
+template <int KW>
+__global__ void __launch_bounds__(EM_THREADS) emit_size_kernel(EmitArgs a) {
+    constexpr int SW = SlotTraits<KW>::WORDS;
+    const u64 slot = (u64)blockIdx.x * EM_THREADS + threadIdx.x;
+    u64 sz = 0, occ = 0;
+    if (slot < a.capacity) {
+        const u64* s = a.table + slot * SW;
+        if (slot_occupied<KW>(s)) {
+            u32 nu, nf;
+            sz = node_record_bytes<KW>(a, slot, s[KW], nu, nf);
+            occ = 1;
+        }
+    }
+    const u64 tb = block_reduce_sum<EM_THREADS>(sz);
+    const u64 tn = block_reduce_sum<EM_THREADS>(occ);
+    if (threadIdx.x == 0) { a.tile_bytes[blockIdx.x] = tb; a.tile_nodes[blockIdx.x] = tn; }
+}
+
+__device__ __forceinline__ uint8_t* put_u32be(uint8_t* p, u32 v) {
+    p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v;
+    return p + 4;
+}
+__device__ __forceinline__ uint8_t* put_u64be(uint8_t* p, u64 v) {
+    p = put_u32be(p, (u32)(v >> 32));
+    return put_u32be(p, (u32)v);
+}
+// big-endian bytes of the k-letter value = the reference's Kmer byte array (Kmer.java:225-242)
+template <int KW>
+__device__ __forceinline__ uint8_t* put_kmer_bytes(uint8_t* p, const u64 (&w)[KW], u32 nb) {
+    for (u32 j = 0; j < nb; ++j) {
+        const u32 byte_idx = nb - 1 - j;  // significance
+        p[j] = (uint8_t)(w[byte_idx >> 3] >> (8 * (byte_idx & 7)));
+    }
+    return p + nb;
+}
+
+// Node.write (Node.java:408-427) + getActiveFields (:466-487) behind the SequenceFile record framing
+// (recordLength, keyLength, VKmer.write VKmer.java:389-391).
+template <int KW>
+__device__ void serialise_node(const EmitArgs& a, u64 slot, const u64* __restrict__ s, u32 rec_bytes, u32 n_unflipped,
+                               u32 n_flipped, uint8_t* p) {
+    const u32 nb = (u32)(a.k + 3) / 4u;
+    u64 key[KW];
+#pragma unroll
+    for (int j = 0; j < KW; ++j) key[j] = s[j];
+    const u64 val = s[KW];
+    const u32 mask = (u32)(val >> MASK_SHIFT);
+    const u64 count = val & COUNT_MASK;
+    p = put_u32be(p, rec_bytes - 8u);
+    p = put_u32be(p, 4u + nb);
+    p = put_u32be(p, (u32)a.k);
+    p = put_kmer_bytes<KW>(p, key, nb);
+    u32 active = 0x80u;  // AVERAGE_COVERAGE always present
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+        if ((mask >> (4 * t)) & 0xfu) active |= 1u << t;
+    if (n_unflipped) active |= 1u << 4;
+    if (n_flipped) active |= 1u << 5;
+    *p++ = (uint8_t)active;
+    for (int t = 0; t < 4; ++t) {
+        const u32 bits = (mask >> (4 * t)) & 0xfu;
+        if (!bits) continue;
+        p = put_u32be(p, (u32)__popc(bits));
+        for (u32 b = 0; b < 4; ++b) {
+            if (!((bits >> b) & 1u)) continue;
+            u64 nk[KW];
+            neighbour_key<KW>(key, a.k, t, b, nk);
+            p = put_u32be(p, (u32)a.k);
+            p = put_kmer_bytes<KW>(p, nk, nb);
+        }
+    }
+    if (n_unflipped | n_flipped) {
+        const Head<KW>* heads = reinterpret_cast<const Head<KW>*>(a.heads);
+        const u32* v = a.hperm + a.hstart[slot];
+        u32 i = 0;
+        for (int set = 0; set < 2; ++set) {
+            const u32 n = set ? n_flipped : n_unflipped;
+            if (!n) continue;
+            *p++ = 1;  // wholeBodyInStream
+            p = put_u32be(p, n);
+            for (u32 e = 0; e < n; ++e, ++i) {
+                const Head<KW>& h = heads[v[i]];
+                *p++ = h.mate_len ? 1 : 0;
+                p = put_u64be(p, h.uuid);
+                p = put_u32be(p, h.this_len);
+                const u32 tb = (h.this_len + 3u) / 4u;
+                for (u32 j = 0; j < tb; ++j) p[j] = a.store[h.this_off + j];
+                p += tb;
+                if (h.mate_len) {
+                    p = put_u32be(p, h.mate_len);
+                    const u32 mb = (h.mate_len + 3u) / 4u;
+                    for (u32 j = 0; j < mb; ++j) p[j] = a.store[h.mate_off + j];
+                    p += mb;
+                }
+            }
+        }
+    }
+    put_u32be(p, __float_as_uint((float)count));  // coverage = float sum of 1.0s (exact to 2^24)
+}
+
+template <int KW>
+__global__ void __launch_bounds__(EM_THREADS) emit_serialise_kernel(EmitArgs a) {
+    constexpr int SW = SlotTraits<KW>::WORDS;
+    extern __shared__ __align__(16) uint8_t stage[];
+    const u64 slot = (u64)blockIdx.x * EM_THREADS + threadIdx.x;
+    u32 sz = 0, nu = 0, nf = 0;
+    const u64* s = nullptr;
+    if (slot < a.capacity) {
+        s = a.table + slot * SW;
+        if (slot_occupied<KW>(s)) sz = node_record_bytes<KW>(a, slot, s[KW], nu, nf);
+    }
+    u64 tile_total, tile_nodes;
+    const u64 ex = block_scan_excl<EM_THREADS>((u64)sz, &tile_total);
+    const u64 nex = block_scan_excl<EM_THREADS>(sz ? 1ull : 0ull, &tile_nodes);
+    const u64 gbase = a.tile_bytes[blockIdx.x];
+    const u32 skew = (u32)(((uintptr_t)(a.out + gbase)) & 15u);
+    const bool staged = tile_total + skew <= (u64)EM_STAGE_BYTES;
+    if (sz) {
+        a.rec_offsets[a.tile_nodes[blockIdx.x] + nex] = gbase + ex;
+        uint8_t* dst = staged ? (stage + skew + ex) : (a.out + gbase + ex);
+        serialise_node<KW>(a, slot, s, sz, nu, nf, dst);
+    }
+    if (!staged) return;
+    __syncthreads();
+    // coalesced copy-out: stage[skew .. skew+tile_total) -> out[gbase ..), 16-byte body, byte edges
+    uint8_t* g0 = a.out + gbase;
+    const u64 head = min((u64)((16u - skew) & 15u), tile_total);
+    const u64 body = (tile_total - head) / 16u;
+    const u64 tail = tile_total - head - body * 16u;
+    if (threadIdx.x < head) g0[threadIdx.x] = stage[skew + threadIdx.x];
+    const uint4* sv = reinterpret_cast<const uint4*>(stage + skew + head);
+    uint4* gv = reinterpret_cast<uint4*>(g0 + head);
+    for (u64 i = threadIdx.x; i < body; i += EM_THREADS) gv[i] = sv[i];
+    if (threadIdx.x < tail) g0[head + body * 16u + threadIdx.x] = stage[skew + head + body * 16u + threadIdx.x];
+}
+
+// R3: KmerPartitionComputerFactory.partition over emitted records (KmerPartitionComputerFactory.java:28-52):
+// h = 1; h = 31*h + (signed byte) over the Kmer field bytes; h < 0 -> -(h+1); h % nParts
+static __global__ void __launch_bounds__(256) partition_records_kernel(const uint8_t* __restrict__ records,
+                                                                const u64* __restrict__ rec_offsets, u64 n_nodes,
+                                                                int n_parts, int* __restrict__ parts) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const uint8_t* r = records + rec_offsets[i];
+    const u32 key_len = ((u32)r[4] << 24) | ((u32)r[5] << 16) | ((u32)r[6] << 8) | (u32)r[7];
+    int h = 1;
+    for (u32 j = 4; j < key_len; ++j) h = 31 * h + (int)(signed char)r[8 + j];  // skip the VKmer length header
+    if (h < 0) h = -(h + 1);
+    parts[i] = h % n_parts;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-callable launch table, one instance per KW (instantiated in gx_kw<N>.cu).
+struct EngineOps {
+    int kw;
+    size_t slot_bytes;
+    size_t head_bytes;
+    void (*init_table)(u64* table, u64 capacity, cudaStream_t st);
+    void (*extract_insert)(const ExtractArgs& a, cudaStream_t st);
+    void (*extract_route)(const ExtractArgs& a, cudaStream_t st);
+    void (*insert_records)(const u64* keys, const unsigned short* meta, const u32* counts, u64 n, u64* table,
+                           u64 capacity, Counters* ctr, cudaStream_t st);
+    void (*rehash)(const u64* old_table, u64 old_capacity, u64* table, u64 capacity, cudaStream_t st);
+    void (*heads_count)(const void* heads, u64 n_heads, const u64* table, u64 capacity, u64* hslot, u32* hcount,
+                        Counters* ctr, cudaStream_t st);
+    void (*heads_sort)(const void* heads, const u64* hslot, u64 n_heads, u64 capacity, const u32* hstart, u32* hcount,
+                       u32* hperm, Counters* ctr, cudaStream_t st);
+    void (*emit_size)(const EmitArgs& a, cudaStream_t st);
+    void (*emit_serialise)(const EmitArgs& a, cudaStream_t st);
+    int (*prepare)();  // one-time function attributes (dynamic shared memory opt-in)
+};
+
+const EngineOps* engine_ops(int kw);
+const EngineOps* engine_ops_kw1();
+const EngineOps* engine_ops_kw2();
+const EngineOps* engine_ops_kw3();
+const EngineOps* engine_ops_kw4();
+
+static inline unsigned grid_for(u64 n, unsigned threads, unsigned max_blocks = 148u * 16u) {
+    u64 b = (n + threads - 1) / threads;
+    if (b < 1) b = 1;
+    if (b > max_blocks) b = max_blocks;
+    return (unsigned)b;
+}
+
+}  // namespace gx

@@ -1,0 +1,210 @@
+// gx_parse.cuh -- line index + line parser kernels (k-mer-width independent).
+//
+// Replaces, for a chunk of text resident in HBM:
+//   * hadoop TextInputFormat record splitting feeding HDFSReadOperatorDescriptor.initialize
+//     (hyracks-hdfs-core/.../dataflow/HDFSReadOperatorDescriptor.java:128-133), and
+//   * the per-line front half of ReadsKeyValueParserFactory.parse
+//     (genomix-hyracks/.../graph/dataflow/ReadsKeyValueParserFactory.java:95-148): split on \t, field
+//     count check, Long.parseLong, [ACGTacgt]+ per mate, the readId / k>=len guards.
+#pragma once
+#include "gx_internal.cuh"
+#include "gx_scan.cuh"
+
+namespace gx {
+
+struct Counters {
+    u64 chunk_lines;     // lines in the current chunk (set by the line-index scan)
+    u64 chunk_reads;     // split mates in the current chunk
+    u64 chunk_occ;       // k-mer occurrences in the current chunk
+    u64 chunk_store;     // read-store bytes reserved by the current chunk
+    u64 lines, reads, bases, occurrences;  // cumulative
+    u64 head_cursor;     // next free index of the heads array
+    u64 store_cursor;    // next free byte of the read store
+    u64 distinct;        // occupied table slots
+    u64 error;           // min over (global line index << 8 | code); ~0 = none
+    u64 heads_missing;   // internal consistency: heads whose key was not found at finish (must stay 0)
+    u64 read_heads;      // ReadHeadInfo entries after de-duplication
+    u64 table_overflow;  // upserts that ran out of probe budget (must stay 0)
+    u64 scratch[2];
+};
+
+enum LineError : u32 {  // low byte of Counters::error; ordered like gx_status
+    LE_FORMAT = 4, LE_NUMBER = 5, LE_TOO_SHORT = 6, LE_READID = 7
+};
+
+static constexpr int LI_THREADS = 256;
+static constexpr int LI_BYTES_PER_THREAD = 32;
+static constexpr int LI_TILE = LI_THREADS * LI_BYTES_PER_THREAD;  // 8 KB of text per CTA
+
+// newline byte-mask of the 32 bytes [pos, pos+32) of text (bit i set <=> text[pos+i] == '\n'), bytes >= n excluded
+__device__ __forceinline__ u32 newline_mask32(const uint8_t* __restrict__ text, u64 n, u64 pos) {
+    u32 m = 0;
+    if (pos >= n) return 0;
+    const uint8_t* p = text + pos;
+    if (pos + 32 <= n && (((uintptr_t)p) & 3) == 0) {
+        const u32* w = reinterpret_cast<const u32*>(p);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const u32 eq = __vcmpeq4(__ldg(w + i), 0x0a0a0a0au);  // 0xff per matching byte
+            m |= ((eq & 1u) | ((eq >> 7) & 2u) | ((eq >> 14) & 4u) | ((eq >> 21) & 8u)) << (4 * i);
+        }
+    } else {
+        const int lim = (int)min((u64)32, n - pos);
+        for (int i = 0; i < lim; ++i) m |= (u32)(__ldg(p + i) == '\n') << i;
+    }
+    return m;
+}
+
+static __global__ void __launch_bounds__(LI_THREADS) count_newlines_kernel(const uint8_t* __restrict__ text, u64 n,
+                                                                    u64* __restrict__ tile_sums) {
+    const u64 pos = (u64)blockIdx.x * LI_TILE + (u64)threadIdx.x * LI_BYTES_PER_THREAD;
+    const u64 c = __popc(newline_mask32(text, n, pos));
+    const u64 tot = block_reduce_sum<LI_THREADS>(c);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+
+// nl_pos[i] = chunk-relative offset of the i-th line terminator. A final unterminated line gets a
+// virtual terminator at offset n (written by the host-side launch of finish_line_index_kernel).
+static __global__ void __launch_bounds__(LI_THREADS) write_newlines_kernel(const uint8_t* __restrict__ text, u64 n,
+                                                                    const u64* __restrict__ tile_base,
+                                                                    u32* __restrict__ nl_pos) {
+    const u64 pos = (u64)blockIdx.x * LI_TILE + (u64)threadIdx.x * LI_BYTES_PER_THREAD;
+    u32 m = newline_mask32(text, n, pos);
+    u64 tot;
+    u64 idx = tile_base[blockIdx.x] + block_scan_excl<LI_THREADS>((u64)__popc(m), &tot);
+    while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        nl_pos[idx++] = (u32)(pos + b);
+    }
+}
+
+// after the tile-sum scan: account for a final unterminated line, publish the line count
+static __global__ void finish_line_index_kernel(const uint8_t* __restrict__ text, u64 n, const u64* __restrict__ total_nl,
+                                         u32* __restrict__ nl_pos, Counters* __restrict__ ctr) {
+    u64 lines = *total_nl;
+    if (n > 0 && text[n - 1] != '\n') { nl_pos[lines] = (u32)n; lines += 1; }
+    ctr->chunk_lines = lines;
+    ctr->chunk_reads = 0;
+    ctr->chunk_occ = 0;
+    ctr->chunk_store = 0;
+}
+
+__device__ __forceinline__ void report_line_error(Counters* ctr, u64 global_line, u32 code) {
+    atomicMin(&ctr->error, (global_line << 8) | (u64)code);
+}
+
+static constexpr int PL_THREADS = 256;
+
+// One thread per line.
+static __global__ void __launch_bounds__(PL_THREADS) parse_lines_kernel(const uint8_t* __restrict__ text,
+                                                                 const u32* __restrict__ nl_pos,
+                                                                 u64 first_global_line, int k,
+                                                                 LineDesc* __restrict__ desc,
+                                                                 Counters* __restrict__ ctr) {
+    const u64 i = (u64)blockIdx.x * PL_THREADS + threadIdx.x;
+    const u64 n_lines = ctr->chunk_lines;  // written by finish_line_index_kernel earlier on the stream
+    u32 n_split = 0, store_bytes = 0;
+    u64 bases = 0, occ = 0;
+    LineDesc d;
+    d.off[0] = d.off[1] = 0; d.len[0] = d.len[1] = 0; d.read_id = 0; d.flags = 0; d.pad = 0;
+    d.store[0] = d.store[1] = 0; d.head_idx[0] = d.head_idx[1] = 0;
+    if (i < n_lines) {
+        const u32 start = (i == 0) ? 0u : nl_pos[i - 1] + 1u;
+        u32 end = nl_pos[i];
+        if (end > start && __ldg(text + end - 1) == '\r') --end;  // hadoop LineReader drops the CR of CRLF
+        // ---- String.split("\t"): field f spans [fs[f], fe[f]); trailing empty fields are dropped
+        u32 fs[3], fe[3];
+        fs[0] = start; fs[1] = fs[2] = end; fe[0] = fe[1] = fe[2] = end;
+        int field = 0, last_nonempty = -1;
+        u32 fstart = start;
+        bool ok0 = true, ok1 = true;  // [ACGTacgt]* so far for fields 1 and 2
+        for (u32 p = start; p <= end; ++p) {
+            const u32 c = (p < end) ? (u32)__ldg(text + p) : (u32)'\t';  // virtual tab closes the last field
+            if (c == '\t') {
+                if (p > fstart) last_nonempty = field;
+                if (field < 3) { fs[field] = fstart; fe[field] = p; }
+                ++field;
+                fstart = p + 1;
+            } else if (field == 1 || field == 2) {
+                bool ok;
+                (void)code_of(c, ok);
+                if (field == 1) ok0 = ok0 && ok; else ok1 = ok1 && ok;
+            }
+        }
+        const int nf = last_nonempty + 1;
+        const u64 gline = first_global_line + i;
+        bool dead = false;
+        if (nf != 2 && nf != 3) { report_line_error(ctr, gline, LE_FORMAT); dead = true; }
+        // ---- Long.parseLong(field 0)
+        u64 mag = 0; bool neg = false;
+        if (!dead) {
+            u32 p = fs[0];
+            const u32 e = fe[0];
+            if (p < e) { const u32 c = __ldg(text + p); if (c == '-' || c == '+') { neg = (c == '-'); ++p; } }
+            bool okn = p < e;
+            for (; p < e && okn; ++p) {
+                const u32 c = __ldg(text + p);
+                if (c < '0' || c > '9') { okn = false; break; }
+                const u64 dgt = c - '0';
+                if (mag > (0x8000000000000000ull - dgt) / 10ull) { okn = false; break; }  // |value| <= 2^63
+                mag = mag * 10ull + dgt;
+            }
+            if (okn && !neg && mag > 0x7fffffffffffffffull) okn = false;
+            if (!okn) { report_line_error(ctr, gline, LE_NUMBER); dead = true; }
+        }
+        if (!dead) {
+            d.read_id = neg ? (u64)(-(long long)mag) : mag;
+            d.off[0] = fs[1]; d.len[0] = fe[1] - fs[1];
+            if (nf == 3) { d.off[1] = fs[2]; d.len[1] = fe[2] - fs[2]; d.flags |= 4u; }
+            const bool v0 = ok0 && d.len[0] > 0;
+            const bool v1 = (nf == 3) && ok1 && d.len[1] > 0;
+            // guards in the order the reference hits them: makeUUID (ReadHeadInfo.java:110-113) then k >= len (:152-155)
+            const bool id_bad = neg || mag >= (1ull << 29);
+            if (v0) {
+                if (id_bad) { report_line_error(ctr, gline, LE_READID); dead = true; }
+                else if ((u32)k >= d.len[0]) { report_line_error(ctr, gline, LE_TOO_SHORT); dead = true; }
+            }
+            if (!dead && v1) {
+                if (id_bad) { report_line_error(ctr, gline, LE_READID); dead = true; }
+                else if ((u32)k >= d.len[1]) { report_line_error(ctr, gline, LE_TOO_SHORT); dead = true; }
+            }
+            if (!dead) {
+                if (v0) { d.flags |= 1u; ++n_split; bases += d.len[0]; occ += d.len[0] - k + 1; }
+                if (v1) { d.flags |= 2u; ++n_split; bases += d.len[1]; occ += d.len[1] - k + 1; }
+                if (n_split) store_bytes = (d.len[0] + 3) / 4 + (d.len[1] + 3) / 4;
+            }
+        }
+    }
+    // ---- reserve head indices and read-store bytes: one atomic pair per CTA
+    u64 tot;
+    const u64 packed = ((u64)store_bytes << 20) | (u64)n_split;
+    const u64 ex = block_scan_excl<PL_THREADS>(packed, &tot);
+    __shared__ u64 base_heads, base_store;
+    if (threadIdx.x == 0) {
+        base_heads = atomicAdd(&ctr->head_cursor, tot & 0xfffffull);
+        base_store = atomicAdd(&ctr->store_cursor, tot >> 20);
+    }
+    const u64 b_sum = block_reduce_sum<PL_THREADS>(bases);
+    const u64 o_sum = block_reduce_sum<PL_THREADS>(occ);
+    if (threadIdx.x == 0) {
+        atomicAdd(&ctr->chunk_reads, tot & 0xfffffull);
+        atomicAdd(&ctr->chunk_store, tot >> 20);
+        atomicAdd(&ctr->chunk_occ, o_sum);
+        atomicAdd(&ctr->reads, tot & 0xfffffull);
+        atomicAdd(&ctr->bases, b_sum);
+        atomicAdd(&ctr->occurrences, o_sum);
+    }
+    __syncthreads();
+    if (i < n_lines) {
+        u64 h = base_heads + (ex & 0xfffffull);
+        u64 s = base_store + (ex >> 20);
+        if (d.flags & 1u) d.head_idx[0] = h++;
+        if (d.flags & 2u) d.head_idx[1] = h++;
+        d.store[0] = s;
+        d.store[1] = s + (d.len[0] + 3) / 4;
+        desc[i] = d;
+    }
+}
+
+}  // namespace gx

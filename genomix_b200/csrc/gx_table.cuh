@@ -1,0 +1,156 @@
+// gx_table.cuh -- lock-free open-addressing hash table keyed on packed canonical k-mers.
+//
+// Replaces the reference's "external sort + pre-clustered group" pair
+// (hyracks-dataflow-std/.../sort/ExternalSortOperatorDescriptor.java:119-194 and
+// .../group/preclustered/PreclusteredGroupWriter.java:76-136 driving
+// genomix-hyracks/.../AggregateKmerAggregateFactory.java:93-144): equal keys meet in one slot, the
+// aggregate (coverage sum, edge-set union) is folded in with atomics.
+//
+// Protocols (linear probing, capacity never above the load limit so a free slot always exists):
+//   KW=1  64-bit atomicCAS on the key word;      value folded with atomicAdd (+ rare atomicOr)
+//   KW=2  128-bit atomicCAS on the key pair;     same
+//   KW>=3 claim the slot by CAS(val: 0 -> LOCK), write key words, publish val with release order;
+//         readers load val with acquire order before they compare key words.
+#pragma once
+#include "gx_internal.cuh"
+
+namespace gx {
+
+__device__ __forceinline__ u64 ld_acquire(const u64* p) {
+    u64 v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(u64* p, u64 v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ u64 ld_relaxed(const u64* p) {
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void ld_relaxed_v2(const u64* p, u64& a, u64& b) {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_relaxed(u64* p, u64 v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ bool cas128(u64* addr, u64 c0, u64 c1, u64 n0, u64 n1, u64& o0, u64& o1) {
+    asm volatile(
+        "{\n\t.reg .b128 c, n, o;\n\t"
+        "mov.b128 c, {%2, %3};\n\t"
+        "mov.b128 n, {%4, %5};\n\t"
+        "atom.relaxed.gpu.global.cas.b128 o, [%6], c, n;\n\t"
+        "mov.b128 {%0, %1}, o;\n\t}"
+        : "=l"(o0), "=l"(o1)
+        : "l"(c0), "l"(c1), "l"(n0), "l"(n1), "l"(addr)
+        : "memory");
+    return o0 == c0 && o1 == c1;
+}
+
+// fold `add` (count in the low 48 bits) and `mask` (16 edge bits) into an occupied slot's value word
+__device__ __forceinline__ void fold_value(u64* val, u64 add, u32 mask) {
+    const u64 old = atomicAdd(val, add);
+    const u64 m = (u64)mask << MASK_SHIFT;
+    if ((old & m) != m) atomicOr(val, m);
+}
+
+// Insert-or-aggregate. Returns the slot index; *is_new set when this call created the slot.
+// A probe budget guards against a full table or a protocol bug turning into a hung GPU: the host keeps the
+// load factor below GROW_LOAD, so the budget is never reached in a correct run; if it is, `capacity` is
+// returned and the caller raises Counters::table_overflow (the job then fails loudly).
+static constexpr u64 PROBE_BUDGET = 1ull << 24;
+
+template <int KW>
+__device__ __forceinline__ u64 table_upsert(u64* __restrict__ table, u64 capacity, const u64 (&key)[KW], u64 add,
+                                            u32 mask, bool& is_new) {
+    constexpr int SW = SlotTraits<KW>::WORDS;
+    u64 slot = slot_of(hash_key<KW>(key), capacity);
+    is_new = false;
+    u64 budget = PROBE_BUDGET;
+    if constexpr (KW == 1) {
+        for (; budget; --budget) {
+            u64* s = table + slot * SW;
+            u64 cur = ld_relaxed(s);
+            if (cur == EMPTY_WORD) {
+                cur = atomicCAS(s, EMPTY_WORD, key[0]);
+                if (cur == EMPTY_WORD) { is_new = true; cur = key[0]; }
+            }
+            if (cur == key[0]) { fold_value(s + 1, add, mask); return slot; }
+            if (++slot == capacity) slot = 0;
+        }
+    } else if constexpr (KW == 2) {
+        for (; budget; --budget) {
+            u64* s = table + slot * SW;
+            u64 c0, c1;
+            ld_relaxed_v2(s, c0, c1);
+            if (c0 == EMPTY_WORD && c1 == EMPTY_WORD) {
+                if (cas128(s, EMPTY_WORD, EMPTY_WORD, key[0], key[1], c0, c1)) { is_new = true; c0 = key[0]; c1 = key[1]; }
+            }
+            if (c0 == key[0] && c1 == key[1]) { fold_value(s + 2, add, mask); return slot; }
+            if (++slot == capacity) slot = 0;
+        }
+    } else {
+        for (; budget; --budget) {
+            u64* s = table + slot * SW;
+            u64* vp = s + KW;
+            u64 v = ld_acquire(vp);
+            if (v == 0) {
+                if (atomicCAS(vp, 0ull, VAL_LOCK) == 0ull) {
+#pragma unroll
+                    for (int i = 0; i < KW; ++i) st_relaxed(s + i, key[i]);
+                    st_release(vp, add | ((u64)mask << MASK_SHIFT));
+                    is_new = true;
+                    return slot;
+                }
+                continue;  // somebody else claimed it: look again
+            }
+            if (v == VAL_LOCK) continue;  // being written: look again
+            bool eq = true;
+#pragma unroll
+            for (int i = 0; i < KW; ++i) eq = eq && (ld_relaxed(s + i) == key[i]);
+            if (eq) { fold_value(vp, add, mask); return slot; }
+            if (++slot == capacity) slot = 0;
+        }
+    }
+    return capacity;  // probe budget exhausted
+}
+
+// Find an existing key (after all inserts are complete). Returns capacity if absent.
+template <int KW>
+__device__ __forceinline__ u64 table_find(const u64* __restrict__ table, u64 capacity, const u64 (&key)[KW]) {
+    constexpr int SW = SlotTraits<KW>::WORDS;
+    u64 slot = slot_of(hash_key<KW>(key), capacity);
+    for (u64 probes = 0; probes < capacity; ++probes) {
+        const u64* s = table + slot * SW;
+        bool eq = true, empty;
+        if constexpr (KW <= 2) {
+            empty = true;
+#pragma unroll
+            for (int i = 0; i < KW; ++i) { u64 c = s[i]; eq = eq && (c == key[i]); empty = empty && (c == EMPTY_WORD); }
+        } else {
+            empty = (s[KW] == 0);
+#pragma unroll
+            for (int i = 0; i < KW; ++i) eq = eq && (s[i] == key[i]);
+        }
+        if (empty) return capacity;
+        if (eq) return slot;
+        if (++slot == capacity) slot = 0;
+    }
+    return capacity;
+}
+
+template <int KW>
+__device__ __forceinline__ bool slot_occupied(const u64* s) {
+    if constexpr (KW <= 2) {
+        bool empty = true;
+#pragma unroll
+        for (int i = 0; i < KW; ++i) empty = empty && (s[i] == EMPTY_WORD);
+        return !empty;
+    } else {
+        return s[KW] != 0;
+    }
+}
+
+}  // namespace gx

@@ -1,0 +1,184 @@
+"""GraphBuilder: thin Python owner of one gx_ctx (include/genomix_gb.h). Every compute call goes through
+the C ABI into the CUDA kernels; nothing here computes on the CPU.
+
+Stands where the reference has GenomixHyracksDriver.runJob + JobGenBuildBrujinGraph
+(genomix-hyracks/.../graph/driver/GenomixHyracksDriver.java:84-135, graph/job/JobGenBuildBrujinGraph.java:79-90).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterator, Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import GxConfig, GxStats, STATUS_NAMES
+
+
+class GenomixError(RuntimeError):
+    """A gx_status < 0; `.status` is the code, the message is what the reference would have thrown."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(f"{STATUS_NAMES.get(status, status)}: {message}")
+        self.status = status
+        self.message = message
+
+
+class GraphBuilder:
+    def __init__(self, kmer_length: int, device: int = 0, rank: int = 0, n_ranks: int = 1,
+                 expected_kmers: int = 0, chunk_bytes: int = 0):
+        self._lib = _lib.load()
+        cfg = GxConfig()
+        cfg.abi_version = _lib.GX_ABI_VERSION
+        cfg.kmer_length = kmer_length
+        cfg.device = device
+        cfg.rank = rank
+        cfg.n_ranks = n_ranks
+        cfg.expected_kmers = expected_kmers
+        cfg.reserved[0] = chunk_bytes
+        self.kmer_length = kmer_length
+        self._ctx = C.c_void_p()
+        st = self._lib.gx_create(C.byref(cfg), C.byref(self._ctx))
+        if st != 0:
+            msg = self._lib.gx_last_error(None).decode()
+            self._ctx = None
+            raise GenomixError(st, msg)
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _check(self, st: int) -> None:
+        if st != 0:
+            raise GenomixError(st, self._lib.gx_last_error(self._ctx).decode())
+
+    def close(self) -> None:
+        if getattr(self, "_ctx", None):
+            self._lib.gx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def reset(self) -> None:
+        self._check(self._lib.gx_reset(self._ctx))
+
+    def set_stream(self, cuda_stream: int) -> None:
+        self._check(self._lib.gx_set_stream(self._ctx, C.c_void_p(cuda_stream)))
+
+    # -- input ------------------------------------------------------------------------------
+    def push_lines(self, text) -> None:
+        """text: bytes / bytearray / numpy uint8 array / pinned torch uint8 tensor (host memory)."""
+        ptr, n, keep = _host_ptr(text)
+        self._check(self._lib.gx_push_lines(self._ctx, ptr, n))
+        del keep
+
+    def push_lines_device(self, dev_ptr: int, n_bytes: int) -> None:
+        self._check(self._lib.gx_push_lines_device(self._ctx, C.c_void_p(dev_ptr), n_bytes))
+
+    def finish(self) -> None:
+        self._check(self._lib.gx_finish(self._ctx))
+
+    # -- output -----------------------------------------------------------------------------
+    @property
+    def num_nodes(self) -> int:
+        return int(self._lib.gx_num_nodes(self._ctx))
+
+    @property
+    def record_bytes(self) -> int:
+        return int(self._lib.gx_record_bytes(self._ctx))
+
+    def records(self) -> bytes:
+        """The whole record stream copied to the host."""
+        n = self.record_bytes
+        if n < 0:
+            raise GenomixError(-9, "records() before finish()")
+        buf = np.empty(max(n, 1), dtype=np.uint8)
+        cursor, used = C.c_uint64(0), C.c_size_t(0)
+        pos = 0
+        while pos < n:
+            self._check(self._lib.gx_next_records(self._ctx, C.byref(cursor), C.c_void_p(buf.ctypes.data + pos), n - pos,
+                                                  C.byref(used)))
+            if used.value == 0:
+                break
+            pos += used.value
+        return buf[:n].tobytes()
+
+    def iter_record_batches(self, batch_bytes: int = 64 << 20) -> Iterator[bytes]:
+        buf = np.empty(batch_bytes, dtype=np.uint8)
+        cursor, used = C.c_uint64(0), C.c_size_t(0)
+        while True:
+            self._check(self._lib.gx_next_records(self._ctx, C.byref(cursor), C.c_void_p(buf.ctypes.data), batch_bytes,
+                                                  C.byref(used)))
+            if used.value == 0:
+                return
+            yield buf[: used.value].tobytes()
+
+    def records_device(self):
+        """(device pointer of the record stream, device pointer of the n_nodes+1 record offsets)."""
+        p, o = C.c_void_p(), C.c_void_p()
+        self._check(self._lib.gx_records_device(self._ctx, C.byref(p), C.byref(o)))
+        return p.value, o.value
+
+    def iter_frames(self, frame_size: int) -> Iterator[bytes]:
+        """Hyracks frames of (Kmer, Node) tuples (FrameTupleAppender.java:57-70 layout)."""
+        frame = np.zeros(frame_size, dtype=np.uint8)
+        cursor, n_tuples = C.c_uint64(0), C.c_int32(0)
+        while True:
+            frame[:] = 0
+            self._check(self._lib.gx_next_frame(self._ctx, C.byref(cursor), C.c_void_p(frame.ctypes.data), frame_size,
+                                                C.byref(n_tuples)))
+            if n_tuples.value == 0:
+                return
+            yield frame.tobytes()
+
+    def partition(self, n_parts: int) -> np.ndarray:
+        """KmerPartitionComputerFactory.partition for every emitted record (Java hash, abs, % n_parts)."""
+        out = np.empty(max(self.num_nodes, 1), dtype=np.int32)
+        self._check(self._lib.gx_partition_records(self._ctx, n_parts, C.c_void_p(out.ctypes.data)))
+        return out[: self.num_nodes]
+
+    # -- introspection ------------------------------------------------------------------------
+    def stats(self) -> dict:
+        s = GxStats()
+        self._check(self._lib.gx_get_stats(self._ctx, C.byref(s)))
+        return s.as_dict()
+
+    def phase_ms(self) -> dict:
+        arr = (C.c_float * 8)()
+        self._check(self._lib.gx_phase_ms(self._ctx, C.byref(arr)))
+        return {"parse": arr[0], "insert": arr[1], "exchange": arr[2], "finish": arr[3], "h2d": arr[4]}
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._lib.gx_kernel_launches(self._ctx))
+
+
+def _host_ptr(obj):
+    """(pointer, n_bytes, keep-alive) for bytes-like / numpy / torch host buffers."""
+    if isinstance(obj, (bytes, bytearray)):
+        arr = np.frombuffer(obj, dtype=np.uint8)
+        return C.c_void_p(arr.ctypes.data), arr.size, (obj, arr)
+    if isinstance(obj, np.ndarray):
+        arr = np.ascontiguousarray(obj).view(np.uint8).reshape(-1)
+        return C.c_void_p(arr.ctypes.data), arr.size, arr
+    if hasattr(obj, "data_ptr"):  # torch tensor on the host
+        if obj.is_cuda:
+            raise TypeError("device tensor passed to push_lines; use push_lines_device")
+        t = obj.contiguous()
+        return C.c_void_p(t.data_ptr()), t.numel() * t.element_size(), t
+    raise TypeError(f"unsupported text buffer type {type(obj)}")
+
+
+def build_graph(kmer_length: int, text, device: int = 0, **kw) -> bytes:
+    """One-call graph build: text lines in, record stream out."""
+    with GraphBuilder(kmer_length, device=device, **kw) as gb:
+        gb.push_lines(text)
+        gb.finish()
+        return gb.records()
