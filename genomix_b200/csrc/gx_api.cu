@@ -68,6 +68,7 @@ struct gx_ctx {
 
     u64* table = nullptr;
     u64 capacity = 0;
+    bool table_live = false;  // false: allocation kept from before gx_reset, content stale
     u64 grows = 0;
 
     DevBuf heads, store;
@@ -235,6 +236,18 @@ int alloc_table(gx_ctx* c, u64 capacity, u64** out) {
 // make room for `incoming` more occurrences (upper bound on new distinct keys)
 int reserve_table(gx_ctx* c, u64 distinct, u64 incoming) {
     const u64 need = distinct + incoming;
+    if (c->table && !c->table_live) {
+        // allocation kept across gx_reset: reuse it if it is big enough, else drop it
+        if ((double)need <= GROW_LOAD * (double)c->capacity) {
+            c->ops->init_table(c->table, c->capacity, c->stream);
+            GX_TRY(check_launch(c, "init_table"));
+            c->table_live = true;
+            return GX_OK;
+        }
+        CUDA_TRY(c, cudaFree(c->table));
+        c->table = nullptr;
+        c->capacity = 0;
+    }
     if (c->table && (double)need <= GROW_LOAD * (double)c->capacity) return GX_OK;
     u64 ncap = std::max<u64>(MIN_CAPACITY, (u64)((double)need / TARGET_LOAD) + 1);
     if (c->table) ncap = std::max<u64>(ncap, c->capacity * 2);
@@ -251,6 +264,7 @@ int reserve_table(gx_ctx* c, u64 distinct, u64 incoming) {
     }
     c->table = nt;
     c->capacity = ncap;
+    c->table_live = true;
     return GX_OK;
 }
 
@@ -390,7 +404,7 @@ int gx_reset(gx_ctx* c) {
     *c->h_ctr = z;
     CUDA_TRY(c, cudaMemcpyAsync(c->d_ctr, c->h_ctr, sizeof z, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    if (c->table) { cudaFree(c->table); c->table = nullptr; c->capacity = 0; }
+    c->table_live = false;  // keep the allocation; it is re-initialised on first use
     if (c->heads.p) CUDA_TRY(c, cudaMemsetAsync(c->heads.p, 0, c->heads.cap, c->stream));
     c->grows = 0;
     c->global_lines = 0;
@@ -506,7 +520,7 @@ int gx_finish(gx_ctx* c) {
     cudaSetDevice(c->cfg.device);
     GX_TRY(sync_counters(c));
     if (c->h_ctr->error != ~0ull) return line_error_to_status(c, c->h_ctr->error);
-    if (!c->table) GX_TRY(reserve_table(c, 0, 0));  // empty job: empty table, zero records
+    if (!c->table || !c->table_live) GX_TRY(reserve_table(c, 0, 0));  // empty job: empty table, zero records
     const u64 cap = c->capacity;
     const u64 n_heads = c->h_ctr->head_cursor;
     const u64 n_tiles = (cap + EM_THREADS - 1) / EM_THREADS;

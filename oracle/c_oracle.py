@@ -1,0 +1,61 @@
+"""ctypes loader of oracle/gx_oracle.c (the fast C twin of oracle.py). TEST INFRASTRUCTURE ONLY --
+see the header of oracle.py for who may import this."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(_HERE, "_bin", "libgx_oracle.so")
+
+
+class OracleStats(C.Structure):
+    _fields_ = [("lines", C.c_uint64), ("reads", C.c_uint64), ("occurrences", C.c_uint64), ("nodes", C.c_uint64),
+                ("err", C.c_int32), ("err_line", C.c_uint64)]
+
+
+class OracleError(Exception):
+    def __init__(self, status, line):
+        super().__init__(f"reference job would fail with status {status} at input line {line}")
+        self.status = status
+        self.line = line
+
+
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(os.path.join(_HERE, "gx_oracle.c")):
+        subprocess.check_call(["make", "-s", "-C", _HERE])
+    return LIB
+
+
+def load():
+    global _lib
+    if _lib is None:
+        lib = C.CDLL(build())
+        lib.gxo_build.restype = C.c_int
+        lib.gxo_build.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                  C.POINTER(OracleStats)]
+        lib.gxo_free.argtypes = [C.c_void_p]
+        lib.gxo_java_partition.restype = C.c_int
+        lib.gxo_java_partition.argtypes = [C.c_char_p, C.c_int, C.c_int]
+        _lib = lib
+    return _lib
+
+
+def build_graph_records(k: int, text, n_threads: int = 1):
+    """Record stream (same framing as the CUDA path) and stats dict for `text` (bytes or numpy uint8 array)."""
+    import numpy as np
+    lib = load()
+    arr = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else np.ascontiguousarray(text)
+    out, out_len, st = C.c_void_p(), C.c_size_t(), OracleStats()
+    rc = lib.gxo_build(C.c_void_p(arr.ctypes.data), arr.size, k, n_threads, C.byref(out), C.byref(out_len), C.byref(st))
+    if rc != 0:
+        raise OracleError(rc, int(st.err_line))
+    try:
+        data = C.string_at(out, out_len.value)
+    finally:
+        lib.gxo_free(out)
+    return data, {"lines": st.lines, "reads": st.reads, "occurrences": st.occurrences, "nodes": st.nodes}

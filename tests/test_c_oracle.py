@@ -1,0 +1,63 @@
+"""The C twin of the oracle (oracle/gx_oracle.c) against the goldens and against oracle.py. CPU only."""
+import numpy as np
+import pytest
+
+from conftest import golden_cases
+from oracle import c_oracle as CO
+from oracle import oracle as O
+
+
+def canon(stream):
+    from genomix_b200 import types as T
+    return T.canonical_records(stream)
+
+
+def py_canon(k, text):
+    from genomix_b200 import types as T
+    return {key: T.Node.read(v, 0)[0].canonical_bytes() for key, v in O.graph_records(k, O.build_graph(k, text)).items()}
+
+
+@pytest.mark.parametrize("name,k,text,expected", golden_cases(), ids=[c[0] for c in golden_cases()])
+@pytest.mark.parametrize("threads", [1, 4])
+def test_c_oracle_reproduces_reference_golden(name, k, text, expected, threads):
+    from genomix_b200 import types as T
+    recs, st = CO.build_graph_records(k, text, threads)
+    O.compare_unordered(expected, T.records_to_text(recs))
+    assert canon(recs) == py_canon(k, text)
+
+
+@pytest.mark.parametrize("k", [1, 4, 21, 32, 55, 91, 128])
+def test_c_oracle_equals_python_oracle(k):
+    rng = np.random.default_rng(k)
+    genome = rng.choice(list(b"ACGT"), size=600).astype(np.uint8)
+    lines = []
+    for i in range(40):
+        L = int(rng.integers(k + 1, k + 50))
+        s = int(rng.integers(0, 600 - L))
+        line = b"%d\t%s" % (4 * i + 2, bytes(genome[s: s + L].tolist()))
+        if i % 3 == 0:
+            L2 = int(rng.integers(k + 1, k + 50))
+            line += b"\t" + bytes(genome[s: s + L2].tolist()[::-1])
+        lines.append(line)
+    text = b"\n".join(lines) + b"\n"
+    want = py_canon(k, text)
+    for threads in (1, 3):
+        recs, st = CO.build_graph_records(k, text, threads)
+        assert canon(recs) == want
+        assert st["nodes"] == len(want)
+
+
+@pytest.mark.parametrize("bad,status", [(b"2\tACGTA\n7\n", -4), (b"x\tACGTA\n", -5), (b"2\tACG\n", -6),
+                                        (b"%d\tACGTA\n" % (1 << 29), -7)])
+def test_c_oracle_errors(bad, status):
+    with pytest.raises(CO.OracleError) as ei:
+        CO.build_graph_records(3, bad, 2)
+    assert ei.value.status == status
+
+
+def test_java_partition_matches():
+    lib = CO.load()
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        key = bytes(rng.integers(0, 256, size=int(rng.integers(1, 24)), dtype=np.uint8).tolist())
+        assert lib.gxo_java_partition(key, len(key), 13) == O.java_partition(key, 13)
