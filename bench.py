@@ -95,7 +95,12 @@ def make_workload(name: str, rank: int, world: int):
     base = synth.CONFIGS[name]
     if world == 1:
         w = base
+        cache = os.environ.get("GX_BENCH_TEXT_CACHE")
+        if cache and os.path.exists(cache + f".{name}.npy"):
+            return w, np.load(cache + f".{name}.npy"), base.n_reads
         text = synth.readid_text(w)
+        if cache:
+            np.save(cache + f".{name}.npy", text)
         return w, text, base.n_reads
     # weak scaling: genome x world, this rank's shard = base.n_reads reads with globally unique ids
     w = synth.Workload(f"{name}x{world}", base.genome_bp * world, base.read_len, base.coverage, base.error, base.k,

@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgenomix_gb.so")
+LIB_PATH = os.environ.get("GENOMIX_GB_LIB") or os.path.join(_HERE, "libgenomix_gb.so")  # env: tuning variants only
 
 GX_ABI_VERSION = 1
 

@@ -85,6 +85,8 @@ struct gx_ctx {
     u64 slab_off = 0, slab_len = 0;
     u64 frame_byte_cursor = 0, frame_rec_cursor = 0;
 
+    void* mg = nullptr;  // MgState (gx_mg.inl) when n_ranks > 1
+
     float phase_ms[PH_COUNT] = {0};
     std::vector<PendingTimer> timers;
     std::vector<cudaEvent_t> event_pool;
@@ -94,6 +96,13 @@ struct gx_ctx {
 namespace {
 
 thread_local std::string g_create_error;
+
+// multi-GPU hooks, defined in gx_mg.inl
+int mg_prepare_route(gx_ctx* c, u64 incoming, ExtractArgs& a);
+int mg_pending(gx_ctx* c, u64* pending);
+int mg_reset(gx_ctx* c);
+void mg_destroy(gx_ctx* c);
+u64 mg_exchanged(gx_ctx* c);
 
 int fail(gx_ctx* c, int code, const char* fmt, ...) {
     char buf[1024];
@@ -320,8 +329,14 @@ int push_chunk_device(gx_ctx* c, const uint8_t* d_text, size_t n) {
         a.store = (uint8_t*)c->store.p;
         a.ctr = c->d_ctr;
         a.n_ranks = 1; a.rank = 0;
-        c->ops->extract_insert(a, c->stream);
-        GX_TRY(check_launch(c, "extract_insert"));
+        if (c->cfg.n_ranks > 1) {
+            GX_TRY(mg_prepare_route(c, h.chunk_occ, a));
+            c->ops->extract_route(a, c->stream);
+            GX_TRY(check_launch(c, "extract_route"));
+        } else {
+            c->ops->extract_insert(a, c->stream);
+            GX_TRY(check_launch(c, "extract_insert"));
+        }
     }
     return GX_OK;
 }
@@ -381,6 +396,8 @@ int gx_create(const gx_config* cfg, gx_ctx** out) {
     c->kw = (c->k + 31) / 32;
     c->ops = engine_ops(c->kw);
     if (cfg->reserved[0]) c->chunk_bytes = (size_t)cfg->reserved[0];
+    // tuning knob: L2 fetch granularity in bytes (32/64/128); random 16-32 B slot accesses want the smallest
+    if (cfg->reserved[1]) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)cfg->reserved[1]);
     auto bail = [&](int code) { g_create_error = c->err; gx_destroy(c); return code; };
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(c, GX_ERR_CUDA, "stream"));
     c->own_stream = true;
@@ -405,6 +422,7 @@ int gx_reset(gx_ctx* c) {
     CUDA_TRY(c, cudaMemcpyAsync(c->d_ctr, c->h_ctr, sizeof z, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     c->table_live = false;  // keep the allocation; it is re-initialised on first use
+    GX_TRY(mg_reset(c));
     if (c->heads.p) CUDA_TRY(c, cudaMemsetAsync(c->heads.p, 0, c->heads.cap, c->stream));
     c->grows = 0;
     c->global_lines = 0;
@@ -423,6 +441,7 @@ void gx_destroy(gx_ctx* c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     drain_timers(c);
+    mg_destroy(c);
     for (auto e : c->event_pool) cudaEventDestroy(e);
     DevBuf* bufs[] = {&c->heads, &c->store, &c->text, &c->nl_pos, &c->desc, &c->tile_sums, &c->hslot, &c->hcount, &c->hstart,
                       &c->hperm, &c->tile_bytes, &c->tile_nodes, &c->records, &c->rec_offsets, &c->parts};
@@ -520,10 +539,16 @@ int gx_finish(gx_ctx* c) {
     cudaSetDevice(c->cfg.device);
     GX_TRY(sync_counters(c));
     if (c->h_ctr->error != ~0ull) return line_error_to_status(c, c->h_ctr->error);
+    if (c->cfg.n_ranks > 1) {
+        u64 pending = 0;
+        GX_TRY(mg_pending(c, &pending));
+        if (pending) return fail(c, GX_ERR_STATE, "gx_finish: %llu routed records not exchanged yet (call gx_mg_exchange on every rank first)",
+                                 (unsigned long long)pending);
+    }
     if (!c->table || !c->table_live) GX_TRY(reserve_table(c, 0, 0));  // empty job: empty table, zero records
     const u64 cap = c->capacity;
     const u64 n_heads = c->h_ctr->head_cursor;
-    const u64 n_tiles = (cap + EM_THREADS - 1) / EM_THREADS;
+    const u64 n_tiles = (cap + EM_TILE - 1) / EM_TILE;
     {
         ScopedPhase ph(c, PH_FINISH);
         if (n_heads) {
@@ -718,6 +743,7 @@ int gx_get_stats(gx_ctx* c, gx_stats* out) {
     out->record_bytes = c->record_bytes;
     out->table_capacity = c->capacity;
     out->table_grows = c->grows;
+    out->exchanged_records = mg_exchanged(c);
     return GX_OK;
 }
 
@@ -732,8 +758,6 @@ int gx_phase_ms(gx_ctx* c, float out_ms[8]) {
 
 uint64_t gx_kernel_launches(gx_ctx* c) { return c ? c->launches : 0; }
 
-int gx_mg_unique_id(uint8_t*) { return GX_ERR_STATE; }
-int gx_mg_init(gx_ctx* c, const uint8_t*) { return fail(c, GX_ERR_STATE, "multi-GPU exchange not built"); }
-int gx_mg_exchange(gx_ctx* c) { return fail(c, GX_ERR_STATE, "multi-GPU exchange not built"); }
-
 }  // extern "C"
+
+#include "gx_mg.inl"

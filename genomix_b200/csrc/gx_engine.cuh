@@ -19,6 +19,15 @@ static constexpr int EX_WARPS = EX_THREADS / 32;
 static constexpr int WIN_BYTES = 512;                       // packed letters per warp window: 2048 letters
 static constexpr int WIN_WORDS = WIN_BYTES / 8 + GX_MAX_KW + 2;
 static constexpr int WIN_POSITIONS = 4 * WIN_BYTES - 160;   // k-mer start positions per window (k <= 128)
+#ifndef GX_EX_BATCH
+#define GX_EX_BATCH 1   // >1: prefetch-batched variant (measured slower on B200: L2 prefetch pulls whole 128 B lines)
+#endif
+#ifndef GX_EX_MIN_BLOCKS
+#define GX_EX_MIN_BLOCKS 4
+#endif
+static constexpr int EX_BATCH = GX_EX_BATCH;                // groups of 30 positions in flight per warp
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 struct ExtractArgs {
     const uint8_t* text; u64 n_text;
@@ -30,10 +39,9 @@ struct ExtractArgs {
     Counters* ctr;
     // routing (multi-GPU) -- unused by the fused kernel
     u32 n_ranks; u32 rank;
-    u64* route_keys;      // [n_ranks][route_cap][KW]
-    unsigned short* route_meta;  // [n_ranks][route_cap]
-    u64 route_cap;
-    u64* route_count;     // [n_ranks]
+    u64* const* route_keys;             // [n_ranks] -> send bucket of key words (KW per record)
+    unsigned short* const* route_meta;  // [n_ranks] -> send bucket of edge masks
+    u64* route_count;                   // [n_ranks] records appended so far
 };
 
 // four text bytes at the 4-byte aligned address `w` -> one packed quad; bytes outside [lo, hi) read as 'A'
@@ -115,8 +123,11 @@ __device__ __forceinline__ u32 edge_bit_prev(bool cur_rev, bool prev_rev, u32 a)
 // One warp per input line; lanes 1..30 own consecutive positions, lanes 0 and 31 are halo lanes that
 // only compute the direction of the neighbouring position.
 template <int KW, bool ROUTE>
-__global__ void __launch_bounds__(EX_THREADS) extract_kernel(ExtractArgs a) {
+__global__ void __launch_bounds__(EX_THREADS, GX_EX_MIN_BLOCKS) extract_kernel(ExtractArgs a) {
     __shared__ u64 sq[EX_WARPS][WIN_WORDS];
+    // per-lane private stash of a batch's keys and masks (lane-major: conflict-free)
+    __shared__ u64 stash_k[(!ROUTE && EX_BATCH > 1) ? EX_WARPS : 1][EX_BATCH][KW][32];
+    __shared__ unsigned short stash_m[(!ROUTE && EX_BATCH > 1) ? EX_WARPS : 1][EX_BATCH][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u64* W = sq[warp];
     uint8_t* Wb = reinterpret_cast<uint8_t*>(W);
@@ -148,63 +159,119 @@ __global__ void __launch_bounds__(EX_THREADS) extract_kernel(ExtractArgs a) {
                 __syncwarp();
                 for (u32 j = lane; j < nwords; j += 32) Wb[j] = (uint8_t)load_quad(aligned + 4 * j, text_lo, text_hi);
                 __syncwarp();
-                for (u32 g = pa; g < pb; g += 30) {
-                    const long long p = (long long)g - 1 + lane;
-                    const bool comp = p >= 0 && p < (long long)npos && p <= (long long)pb;
-                    u64 f[KW], rc[KW];
-                    bool rev = false;
-                    if (comp) {
-                        window_kmer<KW>(W, (u32)(p - lo) + m, k, f);
-                        revcomp_key<KW>(f, k, rc);
-                        rev = !key_le<KW>(f, rc);
-                    }
-                    const u32 dirs = __ballot_sync(0xffffffffu, comp && rev);
-                    const bool active = lane >= 1 && lane <= 30 && p < (long long)pb;
-                    if (active) {
-                        u32 mask = 0;
-                        if (p + 1 < (long long)npos)
-                            mask |= edge_bit_next(rev, (dirs >> (lane + 1)) & 1u, window_letter(W, (u32)(p + k - lo) + m));
-                        if (p > 0)
-                            mask |= edge_bit_prev(rev, (dirs >> (lane - 1)) & 1u, window_letter(W, (u32)(p - 1 - lo) + m));
-                        u64 key[KW];
+                // Groups of 30 positions are handled EX_BATCH at a time: phase A computes every canonical key of the
+                // batch and prefetches its home slot into L2, phase B performs the upserts. Each lane thus keeps up
+                // to EX_BATCH independent table requests in flight instead of one.
+                for (u32 g0 = pa; g0 < pb; g0 += 30 * EX_BATCH) {
+                    u32 acts = 0;
 #pragma unroll
-                        for (int i = 0; i < KW; ++i) key[i] = rev ? rc[i] : f[i];
-                        if (p == 0) {
-                            Head<KW>& h = heads[d.head_idx[mate]];
-#pragma unroll
-                            for (int i = 0; i < KW; ++i) h.key[i] = key[i];
-                            // offset 0 unflipped, K-1 flipped (:165-170); library always 0 (:98-106)
-                            h.uuid = (rev ? ((u64)(k - 1) << 40) : 0ull) | ((u64)mate << 35) | d.read_id;
-                            h.this_off = d.store[mate];
-                            h.mate_off = d.store[1 - mate];
-                            h.this_len = len;
-                            h.mate_len = d.len[1 - mate];
-                            h.flipped = rev ? 1u : 0u;
-                            h.valid = 1u;
+                    for (int j = 0; j < EX_BATCH; ++j) {
+                        const u32 g = g0 + 30 * j;
+                        if (g >= pb) break;  // warp-uniform
+                        const long long p = (long long)g - 1 + lane;
+                        const bool comp = p >= 0 && p < (long long)npos && p <= (long long)pb;
+                        u64 f[KW], rc[KW];
+                        bool rev = false;
+                        if (comp) {
+                            window_kmer<KW>(W, (u32)(p - lo) + m, k, f);
+                            revcomp_key<KW>(f, k, rc);
+                            rev = !key_le<KW>(f, rc);
                         }
-                        if constexpr (!ROUTE) {
+                        const u32 dirs = __ballot_sync(0xffffffffu, comp && rev);
+                        const bool active = lane >= 1 && lane <= 30 && p < (long long)pb;
+                        u32 route_dest = 0xffffffffu, route_mask = 0;
+                        u64 route_key[KW];
+                        (void)route_mask; (void)route_key;
+                        if (active) {
+                            u32 mask = 0;
+                            if (p + 1 < (long long)npos)
+                                mask |= edge_bit_next(rev, (dirs >> (lane + 1)) & 1u, window_letter(W, (u32)(p + k - lo) + m));
+                            if (p > 0)
+                                mask |= edge_bit_prev(rev, (dirs >> (lane - 1)) & 1u, window_letter(W, (u32)(p - 1 - lo) + m));
+                            u64 key[KW];
+#pragma unroll
+                            for (int i = 0; i < KW; ++i) key[i] = rev ? rc[i] : f[i];
+                            if (p == 0) {
+                                Head<KW>& h = heads[d.head_idx[mate]];
+#pragma unroll
+                                for (int i = 0; i < KW; ++i) h.key[i] = key[i];
+                                // offset 0 unflipped, K-1 flipped (:165-170); library always 0 (:98-106)
+                                h.uuid = (rev ? ((u64)(k - 1) << 40) : 0ull) | ((u64)mate << 35) | d.read_id;
+                                h.this_off = d.store[mate];
+                                h.mate_off = d.store[1 - mate];
+                                h.this_len = len;
+                                h.mate_len = d.len[1 - mate];
+                                h.flipped = rev ? 1u : 0u;
+                                h.valid = 1u;
+                            }
+                            if constexpr (!ROUTE) {
+                                if constexpr (EX_BATCH == 1) {
+                                    bool is_new;
+                                    if (table_upsert<KW>(a.table, a.capacity, key, 1ull, mask, is_new) == a.capacity)
+                                        atomicAdd(&a.ctr->table_overflow, 1ull);
+                                    new_slots += is_new ? 1u : 0u;
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < KW; ++i) stash_k[warp][j][i][lane] = key[i];
+                                    stash_m[warp][j][lane] = (unsigned short)mask;
+                                    prefetch_l2(a.table + slot_of(hash_key<KW>(key), a.capacity) * SlotTraits<KW>::WORDS);
+                                    acts |= 1u << j;
+                                }
+                            } else {
+                                // multi-GPU: own keys go straight into the table, the others are appended to their
+                                // owner's send bucket (one atomic per warp and destination)
+                                const u32 owner = owner_of(hash_key<KW>(key), a.n_ranks);
+                                route_dest = owner;
+                                if (owner == a.rank) {
+                                    bool is_new;
+                                    if (table_upsert<KW>(a.table, a.capacity, key, 1ull, mask, is_new) == a.capacity)
+                                        atomicAdd(&a.ctr->table_overflow, 1ull);
+                                    new_slots += is_new ? 1u : 0u;
+                                    route_dest = 0xffffffffu;
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < KW; ++i) route_key[i] = key[i];
+                                    route_mask = mask;
+                                }
+                            }
+                        }
+                        if constexpr (ROUTE) {
+                            // warp-aggregated append: lanes with the same destination share one reservation
+                            const u32 live = __ballot_sync(0xffffffffu, route_dest != 0xffffffffu);
+                            if (route_dest != 0xffffffffu) {
+                                const u32 peers = __match_any_sync(live, route_dest);
+                                const int leader = __ffs(peers) - 1;
+                                u64 base = 0;
+                                if (lane == leader) base = atomicAdd(a.route_count + route_dest, (u64)__popc(peers));
+                                base = __shfl_sync(peers, base, leader);
+                                const u64 idx = base + __popc(peers & ((1u << lane) - 1u));
+                                u64* kd = a.route_keys[route_dest] + idx * KW;
+#pragma unroll
+                                for (int i = 0; i < KW; ++i) kd[i] = route_key[i];
+                                a.route_meta[route_dest][idx] = (unsigned short)route_mask;
+                            }
+                        }
+                    }
+                    if constexpr (!ROUTE && EX_BATCH > 1) {
+#pragma unroll
+                        for (int j = 0; j < EX_BATCH; ++j) {
+                            if (!((acts >> j) & 1u)) continue;
+                            u64 key[KW];
+#pragma unroll
+                            for (int i = 0; i < KW; ++i) key[i] = stash_k[warp][j][i][lane];
                             bool is_new;
-                            if (table_upsert<KW>(a.table, a.capacity, key, 1ull, mask, is_new) == a.capacity)
+                            if (table_upsert<KW>(a.table, a.capacity, key, 1ull, stash_m[warp][j][lane], is_new) == a.capacity)
                                 atomicAdd(&a.ctr->table_overflow, 1ull);
                             new_slots += is_new ? 1u : 0u;
-                        } else {
-                            const u32 owner = owner_of(hash_key<KW>(key), a.n_ranks);
-                            const u64 idx = atomicAdd(a.route_count + owner, 1ull);
-                            u64* kd = a.route_keys + ((u64)owner * a.route_cap + idx) * KW;
-#pragma unroll
-                            for (int i = 0; i < KW; ++i) kd[i] = key[i];
-                            a.route_meta[(u64)owner * a.route_cap + idx] = (unsigned short)mask;
                         }
                     }
                 }
             }
         }
     }
-    if constexpr (!ROUTE) {
 #pragma unroll
-        for (int dlt = 16; dlt > 0; dlt >>= 1) new_slots += __shfl_xor_sync(0xffffffffu, new_slots, dlt);
-        if (lane == 0 && new_slots) atomicAdd(&a.ctr->distinct, (u64)new_slots);
-    }
+    for (int dlt = 16; dlt > 0; dlt >>= 1) new_slots += __shfl_xor_sync(0xffffffffu, new_slots, dlt);
+    if (lane == 0 && new_slots) atomicAdd(&a.ctr->distinct, (u64)new_slots);
 }
 
 // K2x: upsert pre-extracted (key, mask, count) records (received from other GPUs, or partial aggregates).
@@ -268,14 +335,14 @@ __global__ void __launch_bounds__(256) heads_count_kernel(const Head<KW>* __rest
     if (i >= n_heads) return;
     const Head<KW>& h = heads[i];
     u64 slot = capacity;
-    if (h.valid) {
+    if (h.valid == 1u) {
         u64 key[KW];
 #pragma unroll
         for (int j = 0; j < KW; ++j) key[j] = h.key[j];
         slot = table_find<KW>(table, capacity, key);
     }
     hslot[i] = slot;
-    if (slot == capacity) { atomicAdd(&ctr->heads_missing, 1ull); return; }
+    if (slot == capacity) { if (h.valid != 2u) atomicAdd(&ctr->heads_missing, 1ull); return; }
     atomicAdd(hcount + slot, 1u);
 }
 
@@ -362,9 +429,62 @@ __global__ void __launch_bounds__(256) heads_sort_kernel(const Head<KW>* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
+// Multi-GPU read-head routing: a ReadHeadInfo belongs to the node of the read's first k-mer, so it follows
+// that key to its owner GPU together with the packed read and mate sequences it will serialise.
+struct HeadRouteArgs {
+    void* heads; u64 first, n;              // local heads [first, first+n) created since the last exchange
+    const uint8_t* store;                   // local read store
+    u32 n_ranks, rank;
+    void* const* send_heads;                // [n_ranks] -> Head<KW> send buckets
+    uint8_t* const* send_store;             // [n_ranks] -> packed sequence bytes that go with them
+    u64* send_head_count; u64* send_store_bytes;  // [n_ranks]
+};
+
+template <int KW>
+__global__ void __launch_bounds__(256) route_heads_kernel(HeadRouteArgs a) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    Head<KW>& h = reinterpret_cast<Head<KW>*>(a.heads)[a.first + i];
+    if (h.valid != 1u) return;
+    u64 key[KW];
+#pragma unroll
+    for (int j = 0; j < KW; ++j) key[j] = h.key[j];
+    const u32 owner = owner_of(hash_key<KW>(key), a.n_ranks);
+    if (owner == a.rank) return;
+    const u32 tb = (h.this_len + 3u) / 4u, mb = (h.mate_len + 3u) / 4u;
+    const u64 idx = atomicAdd(a.send_head_count + owner, 1ull);
+    const u64 off = atomicAdd(a.send_store_bytes + owner, (u64)(tb + mb));
+    uint8_t* dst = a.send_store[owner] + off;
+    for (u32 j = 0; j < tb; ++j) dst[j] = a.store[h.this_off + j];
+    for (u32 j = 0; j < mb; ++j) dst[tb + j] = a.store[h.mate_off + j];
+    Head<KW> out = h;
+    out.this_off = off;        // relative to the segment this rank sends; the receiver rebases
+    out.mate_off = off + tb;
+    reinterpret_cast<Head<KW>*>(a.send_heads[owner])[idx] = out;
+    h.valid = 2u;              // moved away: ignored by this rank's emit
+}
+
+template <int KW>
+__global__ void __launch_bounds__(256) rebase_heads_kernel(void* heads, u64 first, u64 n, u64 store_base) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Head<KW>& h = reinterpret_cast<Head<KW>*>(heads)[first + i];
+    h.this_off += store_base;
+    h.mate_off += store_base;
+}
+
+static __global__ void bump_cursors_kernel(Counters* ctr, u64 heads, u64 store_bytes) {
+    ctr->head_cursor += heads;
+    ctr->store_cursor += store_bytes;
+}
+
+// ---------------------------------------------------------------------------------------------
 // K3b: sizes and serialisation of `VKmer key | Node` records.
-static constexpr int EM_THREADS = 1024;               // slots per tile
-static constexpr int EM_STAGE_BYTES = 96 * 1024;      // shared-memory staging of a tile's records
+static constexpr int EM_THREADS = 256;
+static constexpr int EM_PER_THREAD = 4;
+static constexpr int EM_TILE = EM_THREADS * EM_PER_THREAD;  // slots per tile (CTA)
+static constexpr int EM_STAGE_BYTES = 60 * 1024;             // shared-memory staging of a tile's records
+static constexpr int EM_SMEM_BYTES = EM_STAGE_BYTES + 16 + EM_TILE * 12;
 
 struct EmitArgs {
     const u64* table; u64 capacity; int k;
@@ -405,17 +525,22 @@ __device__ __forceinline__ u32 node_record_bytes(const EmitArgs& a, u64 slot, u6
     return sz;
 }
 
+// Tile = EM_TILE consecutive slots per CTA; thread t owns slots 4t..4t+3 of the tile (contiguous 16-byte loads).
 template <int KW>
 __global__ void __launch_bounds__(EM_THREADS) emit_size_kernel(EmitArgs a) {
     constexpr int SW = SlotTraits<KW>::WORDS;
-    const u64 slot = (u64)blockIdx.x * EM_THREADS + threadIdx.x;
+    const u64 slot0 = (u64)blockIdx.x * EM_TILE + (u64)threadIdx.x * EM_PER_THREAD;
     u64 sz = 0, occ = 0;
-    if (slot < a.capacity) {
-        const u64* s = a.table + slot * SW;
-        if (slot_occupied<KW>(s)) {
-            u32 nu, nf;
-            sz = node_record_bytes<KW>(a, slot, s[KW], nu, nf);
-            occ = 1;
+#pragma unroll
+    for (int i = 0; i < EM_PER_THREAD; ++i) {
+        const u64 slot = slot0 + i;
+        if (slot < a.capacity) {
+            const u64* s = a.table + slot * SW;
+            if (slot_occupied<KW>(s)) {
+                u32 nu, nf;
+                sz += node_record_bytes<KW>(a, slot, s[KW], nu, nf);
+                occ += 1;
+            }
         }
     }
     const u64 tb = block_reduce_sum<EM_THREADS>(sz);
@@ -423,29 +548,74 @@ __global__ void __launch_bounds__(EM_THREADS) emit_size_kernel(EmitArgs a) {
     if (threadIdx.x == 0) { a.tile_bytes[blockIdx.x] = tb; a.tile_nodes[blockIdx.x] = tn; }
 }
 
-__device__ __forceinline__ uint8_t* put_u32be(uint8_t* p, u32 v) {
-    p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v;
-    return p + 4;
-}
-__device__ __forceinline__ uint8_t* put_u64be(uint8_t* p, u64 v) {
-    p = put_u32be(p, (u32)(v >> 32));
-    return put_u32be(p, (u32)v);
-}
+// Byte sink that assembles the stream in a 32-bit register and stores whole aligned words; only the first
+// and last (partial) words of a record, which it shares with its neighbours, go out as byte stores.
+struct WordWriter {
+    uint8_t* base;  // 4-byte aligned origin (shared-memory stage or the global record buffer)
+    u32 pos;        // byte offset from base of the next byte
+    u32 acc;        // bytes of the current word gathered so far (first stream byte in the low lane)
+    u32 first;      // != 0 only while in the record's first word: index of our first byte inside it
+
+    __device__ __forceinline__ void init(uint8_t* dst) {
+        const u32 mis = (u32)((uintptr_t)dst & 3u);
+        base = dst - mis;
+        pos = mis;
+        acc = 0;
+        first = mis;
+    }
+    __device__ __forceinline__ void flush_word(u32 end) {  // the word [end-4, end) is complete
+        uint8_t* w = base + end - 4;
+        if (first) {
+            for (u32 i = first; i < 4; ++i) w[i] = (uint8_t)(acc >> (8 * i));
+            first = 0;
+        } else {
+            *reinterpret_cast<u32*>(w) = acc;
+        }
+        acc = 0;
+    }
+    __device__ __forceinline__ void put8(u32 v) {
+        acc |= (v & 0xffu) << (8u * (pos & 3u));
+        ++pos;
+        if ((pos & 3u) == 0) flush_word(pos);
+    }
+    __device__ __forceinline__ void put32be(u32 v) {
+        const u32 le = __byte_perm(v, 0, 0x0123);  // byte-swapped: first stream byte in the low lane
+        const u32 sh = 8u * (pos & 3u);
+        acc |= le << sh;
+        const u32 keep = sh ? (le >> (32u - sh)) : 0u;
+        pos += 4;
+        flush_word(pos & ~3u);
+        acc = keep;
+    }
+    __device__ __forceinline__ void put64be(u64 v) { put32be((u32)(v >> 32)); put32be((u32)v); }
+    __device__ __forceinline__ void finish() {  // bytes of a last, incomplete word
+        const u32 n = pos & 3u;
+        uint8_t* w = base + (pos & ~3u);
+        for (u32 i = first; i < n; ++i) w[i] = (uint8_t)(acc >> (8 * i));
+    }
+};
+
 // big-endian bytes of the k-letter value = the reference's Kmer byte array (Kmer.java:225-242)
 template <int KW>
-__device__ __forceinline__ uint8_t* put_kmer_bytes(uint8_t* p, const u64 (&w)[KW], u32 nb) {
-    for (u32 j = 0; j < nb; ++j) {
-        const u32 byte_idx = nb - 1 - j;  // significance
-        p[j] = (uint8_t)(w[byte_idx >> 3] >> (8 * (byte_idx & 7)));
-    }
-    return p + nb;
+__device__ __forceinline__ void put_kmer_bytes(WordWriter& w, const u64 (&x)[KW], u32 nb) {
+    // most significant byte first: the (nb & 3) bytes of the partial top 32-bit chunk, then whole chunks.
+    // Fully unrolled with predicates so that x[] stays in registers.
+    const u32 full = nb >> 2, part = nb & 3u;
+    u32 top = 0;
+#pragma unroll
+    for (int c = 0; c < 2 * KW; ++c)
+        if ((u32)c == full) top = (u32)(x[c >> 1] >> (32 * (c & 1)));
+    for (u32 i = part; i-- > 0;) w.put8(top >> (8 * i));
+#pragma unroll
+    for (int c = 2 * KW - 1; c >= 0; --c)
+        if ((u32)c < full) w.put32be((u32)(x[c >> 1] >> (32 * (c & 1))));
 }
 
 // Node.write (Node.java:408-427) + getActiveFields (:466-487) behind the SequenceFile record framing
 // (recordLength, keyLength, VKmer.write VKmer.java:389-391).
 template <int KW>
 __device__ void serialise_node(const EmitArgs& a, u64 slot, const u64* __restrict__ s, u32 rec_bytes, u32 n_unflipped,
-                               u32 n_flipped, uint8_t* p) {
+                               u32 n_flipped, uint8_t* dst) {
     const u32 nb = (u32)(a.k + 3) / 4u;
     u64 key[KW];
 #pragma unroll
@@ -453,27 +623,29 @@ __device__ void serialise_node(const EmitArgs& a, u64 slot, const u64* __restric
     const u64 val = s[KW];
     const u32 mask = (u32)(val >> MASK_SHIFT);
     const u64 count = val & COUNT_MASK;
-    p = put_u32be(p, rec_bytes - 8u);
-    p = put_u32be(p, 4u + nb);
-    p = put_u32be(p, (u32)a.k);
-    p = put_kmer_bytes<KW>(p, key, nb);
+    WordWriter w;
+    w.init(dst);
+    w.put32be(rec_bytes - 8u);
+    w.put32be(4u + nb);
+    w.put32be((u32)a.k);
+    put_kmer_bytes<KW>(w, key, nb);
     u32 active = 0x80u;  // AVERAGE_COVERAGE always present
 #pragma unroll
     for (int t = 0; t < 4; ++t)
         if ((mask >> (4 * t)) & 0xfu) active |= 1u << t;
     if (n_unflipped) active |= 1u << 4;
     if (n_flipped) active |= 1u << 5;
-    *p++ = (uint8_t)active;
+    w.put8(active);
     for (int t = 0; t < 4; ++t) {
         const u32 bits = (mask >> (4 * t)) & 0xfu;
         if (!bits) continue;
-        p = put_u32be(p, (u32)__popc(bits));
+        w.put32be((u32)__popc(bits));
         for (u32 b = 0; b < 4; ++b) {
             if (!((bits >> b) & 1u)) continue;
             u64 nk[KW];
             neighbour_key<KW>(key, a.k, t, b, nk);
-            p = put_u32be(p, (u32)a.k);
-            p = put_kmer_bytes<KW>(p, nk, nb);
+            w.put32be((u32)a.k);
+            put_kmer_bytes<KW>(w, nk, nb);
         }
     }
     if (n_unflipped | n_flipped) {
@@ -483,49 +655,79 @@ __device__ void serialise_node(const EmitArgs& a, u64 slot, const u64* __restric
         for (int set = 0; set < 2; ++set) {
             const u32 n = set ? n_flipped : n_unflipped;
             if (!n) continue;
-            *p++ = 1;  // wholeBodyInStream
-            p = put_u32be(p, n);
+            w.put8(1);  // wholeBodyInStream
+            w.put32be(n);
             for (u32 e = 0; e < n; ++e, ++i) {
                 const Head<KW>& h = heads[v[i]];
-                *p++ = h.mate_len ? 1 : 0;
-                p = put_u64be(p, h.uuid);
-                p = put_u32be(p, h.this_len);
+                w.put8(h.mate_len ? 1 : 0);
+                w.put64be(h.uuid);
+                w.put32be(h.this_len);
                 const u32 tb = (h.this_len + 3u) / 4u;
-                for (u32 j = 0; j < tb; ++j) p[j] = a.store[h.this_off + j];
-                p += tb;
+                for (u32 j = 0; j < tb; ++j) w.put8(a.store[h.this_off + j]);
                 if (h.mate_len) {
-                    p = put_u32be(p, h.mate_len);
+                    w.put32be(h.mate_len);
                     const u32 mb = (h.mate_len + 3u) / 4u;
-                    for (u32 j = 0; j < mb; ++j) p[j] = a.store[h.mate_off + j];
-                    p += mb;
+                    for (u32 j = 0; j < mb; ++j) w.put8(a.store[h.mate_off + j]);
                 }
             }
         }
     }
-    put_u32be(p, __float_as_uint((float)count));  // coverage = float sum of 1.0s (exact to 2^24)
+    w.put32be(__float_as_uint((float)count));  // coverage = float sum of 1.0s (exact to 2^24)
+    w.finish();
 }
 
+// Phase 1: every thread sizes its 4 slots, a block scan turns sizes into byte offsets and node ranks, and the
+// occupied slots are written to a dense shared-memory work list. Phase 2: threads take nodes from the dense
+// list (full warps instead of one live lane in three) and serialise into the staging area, which the CTA then
+// copies out with aligned 16-byte stores.
 template <int KW>
 __global__ void __launch_bounds__(EM_THREADS) emit_serialise_kernel(EmitArgs a) {
     constexpr int SW = SlotTraits<KW>::WORDS;
-    extern __shared__ __align__(16) uint8_t stage[];
-    const u64 slot = (u64)blockIdx.x * EM_THREADS + threadIdx.x;
-    u32 sz = 0, nu = 0, nf = 0;
-    const u64* s = nullptr;
-    if (slot < a.capacity) {
-        s = a.table + slot * SW;
-        if (slot_occupied<KW>(s)) sz = node_record_bytes<KW>(a, slot, s[KW], nu, nf);
+    extern __shared__ __align__(16) uint8_t smem_dyn[];
+    uint2* work = reinterpret_cast<uint2*>(smem_dyn);                 // [EM_TILE] (local slot | nu<<12 | nf<<22, byte offset)
+    u32* work_sz = reinterpret_cast<u32*>(smem_dyn + EM_TILE * 8);    // [EM_TILE] record bytes
+    uint8_t* stage = smem_dyn + EM_TILE * 12;
+    const u64 tile0 = (u64)blockIdx.x * EM_TILE;
+    const u32 local0 = threadIdx.x * EM_PER_THREAD;
+    u32 sz[EM_PER_THREAD], nu[EM_PER_THREAD], nf[EM_PER_THREAD];
+    u32 my_bytes = 0, my_nodes = 0;
+#pragma unroll
+    for (int i = 0; i < EM_PER_THREAD; ++i) {
+        sz[i] = nu[i] = nf[i] = 0;
+        const u64 slot = tile0 + local0 + i;
+        if (slot < a.capacity) {
+            const u64* s = a.table + slot * SW;
+            if (slot_occupied<KW>(s)) sz[i] = node_record_bytes<KW>(a, slot, s[KW], nu[i], nf[i]);
+        }
+        my_bytes += sz[i];
+        my_nodes += sz[i] ? 1u : 0u;
     }
     u64 tile_total, tile_nodes;
-    const u64 ex = block_scan_excl<EM_THREADS>((u64)sz, &tile_total);
-    const u64 nex = block_scan_excl<EM_THREADS>(sz ? 1ull : 0ull, &tile_nodes);
+    u64 ex = block_scan_excl<EM_THREADS>((u64)my_bytes, &tile_total);
+    u64 nex = block_scan_excl<EM_THREADS>((u64)my_nodes, &tile_nodes);
     const u64 gbase = a.tile_bytes[blockIdx.x];
+    const u64 nbase = a.tile_nodes[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < EM_PER_THREAD; ++i) {
+        if (!sz[i]) continue;
+        a.rec_offsets[nbase + nex] = gbase + ex;
+        // nu/nf only steer the head loops; they are re-derived exactly in phase 2 when they do not fit
+        work[nex] = make_uint2((local0 + i) | (min(nu[i], 1023u) << 12) | (min(nf[i], 1023u) << 22), (u32)ex);
+        work_sz[nex] = sz[i];
+        ex += sz[i];
+        ++nex;
+    }
     const u32 skew = (u32)(((uintptr_t)(a.out + gbase)) & 15u);
     const bool staged = tile_total + skew <= (u64)EM_STAGE_BYTES;
-    if (sz) {
-        a.rec_offsets[a.tile_nodes[blockIdx.x] + nex] = gbase + ex;
-        uint8_t* dst = staged ? (stage + skew + ex) : (a.out + gbase + ex);
-        serialise_node<KW>(a, slot, s, sz, nu, nf, dst);
+    __syncthreads();
+    for (u32 n = threadIdx.x; n < (u32)tile_nodes; n += EM_THREADS) {
+        const uint2 wk = work[n];
+        const u64 slot = tile0 + (wk.x & 0xfffu);
+        u32 cu = (wk.x >> 12) & 0x3ffu, cf = (wk.x >> 22) & 0x3ffu;
+        const u64* s = a.table + slot * SW;
+        if (cu == 1023u || cf == 1023u) (void)node_record_bytes<KW>(a, slot, s[KW], cu, cf);
+        uint8_t* dst = staged ? (stage + skew + wk.y) : (a.out + gbase + wk.y);
+        serialise_node<KW>(a, slot, s, work_sz[n], cu, cf, dst);
     }
     if (!staged) return;
     __syncthreads();
@@ -574,6 +776,8 @@ struct EngineOps {
                        u32* hperm, Counters* ctr, cudaStream_t st);
     void (*emit_size)(const EmitArgs& a, cudaStream_t st);
     void (*emit_serialise)(const EmitArgs& a, cudaStream_t st);
+    void (*route_heads)(const HeadRouteArgs& a, cudaStream_t st);
+    void (*rebase_heads)(void* heads, u64 first, u64 n, u64 store_base, cudaStream_t st);
     int (*prepare)();  // one-time function attributes (dynamic shared memory opt-in)
 };
 

@@ -35,13 +35,21 @@ void l_heads_sort(const void* heads, const u64* hslot, u64 n_heads, u64 capacity
         reinterpret_cast<const Head<KW>*>(heads), hslot, n_heads, capacity, hstart, hcount, hperm, ctr);
 }
 void l_emit_size(const EmitArgs& a, cudaStream_t st) {
-    emit_size_kernel<KW><<<(unsigned)((a.capacity + EM_THREADS - 1) / EM_THREADS), EM_THREADS, 0, st>>>(a);
+    emit_size_kernel<KW><<<(unsigned)((a.capacity + EM_TILE - 1) / EM_TILE), EM_THREADS, 0, st>>>(a);
 }
 void l_emit_serialise(const EmitArgs& a, cudaStream_t st) {
-    emit_serialise_kernel<KW><<<(unsigned)((a.capacity + EM_THREADS - 1) / EM_THREADS), EM_THREADS, EM_STAGE_BYTES, st>>>(a);
+    emit_serialise_kernel<KW><<<(unsigned)((a.capacity + EM_TILE - 1) / EM_TILE), EM_THREADS, EM_SMEM_BYTES, st>>>(a);
+}
+void l_route_heads(const HeadRouteArgs& a, cudaStream_t st) {
+    if (a.n == 0) return;
+    route_heads_kernel<KW><<<(unsigned)((a.n + 255) / 256), 256, 0, st>>>(a);
+}
+void l_rebase_heads(void* heads, u64 first, u64 n, u64 store_base, cudaStream_t st) {
+    if (n == 0) return;
+    rebase_heads_kernel<KW><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(heads, first, n, store_base);
 }
 int l_prepare() {
-    return (int)cudaFuncSetAttribute(emit_serialise_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, EM_STAGE_BYTES);
+    return (int)cudaFuncSetAttribute(emit_serialise_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, EM_SMEM_BYTES);
 }
 
 const EngineOps OPS = {KW,
@@ -56,6 +64,8 @@ const EngineOps OPS = {KW,
                        l_heads_sort,
                        l_emit_size,
                        l_emit_serialise,
+                       l_route_heads,
+                       l_rebase_heads,
                        l_prepare};
 }  // namespace
 

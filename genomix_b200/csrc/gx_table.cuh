@@ -32,6 +32,11 @@ __device__ __forceinline__ u64 ld_relaxed(const u64* p) {
 __device__ __forceinline__ void ld_relaxed_v2(const u64* p, u64& a, u64& b) {
     asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
+__device__ __forceinline__ void ld_relaxed_v4(const u64* p, u64& a, u64& b, u64& c, u64& d) {
+    // two 16-byte halves of one 32-byte sector, issued back to back
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%4];\n\tld.relaxed.gpu.global.v2.u64 {%2, %3}, [%4+16];"
+                 : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory");
+}
 __device__ __forceinline__ void st_relaxed(u64* p, u64 v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -49,11 +54,13 @@ __device__ __forceinline__ bool cas128(u64* addr, u64 c0, u64 c1, u64 n0, u64 n1
     return o0 == c0 && o1 == c1;
 }
 
-// fold `add` (count in the low 48 bits) and `mask` (16 edge bits) into an occupied slot's value word
-__device__ __forceinline__ void fold_value(u64* val, u64 add, u32 mask) {
-    const u64 old = atomicAdd(val, add);
+// Fold `add` (count in the low 48 bits) and `mask` (16 edge bits) into an occupied slot's value word.
+// `seen` is any earlier snapshot of that value word: edge bits only ever get set, so bits already present in
+// the snapshot need no atomicOr. Neither atomic's result is used, so both compile to fire-and-forget RED.
+__device__ __forceinline__ void fold_value(u64* val, u64 add, u32 mask, u64 seen) {
+    atomicAdd(val, add);
     const u64 m = (u64)mask << MASK_SHIFT;
-    if ((old & m) != m) atomicOr(val, m);
+    if ((seen & m) != m) atomicOr(val, m);
 }
 
 // Insert-or-aggregate. Returns the slot index; *is_new set when this call created the slot.
@@ -72,23 +79,26 @@ __device__ __forceinline__ u64 table_upsert(u64* __restrict__ table, u64 capacit
     if constexpr (KW == 1) {
         for (; budget; --budget) {
             u64* s = table + slot * SW;
-            u64 cur = ld_relaxed(s);
+            u64 cur, seen;
+            ld_relaxed_v2(s, cur, seen);  // key and value word: one 16-byte request
             if (cur == EMPTY_WORD) {
                 cur = atomicCAS(s, EMPTY_WORD, key[0]);
                 if (cur == EMPTY_WORD) { is_new = true; cur = key[0]; }
+                seen = 0;
             }
-            if (cur == key[0]) { fold_value(s + 1, add, mask); return slot; }
+            if (cur == key[0]) { fold_value(s + 1, add, mask, seen); return slot; }
             if (++slot == capacity) slot = 0;
         }
     } else if constexpr (KW == 2) {
         for (; budget; --budget) {
             u64* s = table + slot * SW;
-            u64 c0, c1;
-            ld_relaxed_v2(s, c0, c1);
+            u64 c0, c1, seen, pad;
+            ld_relaxed_v4(s, c0, c1, seen, pad);  // the whole 32-byte slot (one sector)
             if (c0 == EMPTY_WORD && c1 == EMPTY_WORD) {
                 if (cas128(s, EMPTY_WORD, EMPTY_WORD, key[0], key[1], c0, c1)) { is_new = true; c0 = key[0]; c1 = key[1]; }
+                seen = 0;
             }
-            if (c0 == key[0] && c1 == key[1]) { fold_value(s + 2, add, mask); return slot; }
+            if (c0 == key[0] && c1 == key[1]) { fold_value(s + 2, add, mask, seen); return slot; }
             if (++slot == capacity) slot = 0;
         }
     } else {
@@ -110,7 +120,7 @@ __device__ __forceinline__ u64 table_upsert(u64* __restrict__ table, u64 capacit
             bool eq = true;
 #pragma unroll
             for (int i = 0; i < KW; ++i) eq = eq && (ld_relaxed(s + i) == key[i]);
-            if (eq) { fold_value(vp, add, mask); return slot; }
+            if (eq) { fold_value(vp, add, mask, v); return slot; }
             if (++slot == capacity) slot = 0;
         }
     }

@@ -7,6 +7,7 @@ Stands where the reference has GenomixHyracksDriver.runJob + JobGenBuildBrujinGr
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Iterator, Optional
 
 import numpy as np
@@ -26,7 +27,7 @@ class GenomixError(RuntimeError):
 
 class GraphBuilder:
     def __init__(self, kmer_length: int, device: int = 0, rank: int = 0, n_ranks: int = 1,
-                 expected_kmers: int = 0, chunk_bytes: int = 0):
+                 expected_kmers: int = 0, chunk_bytes: int = 0, l2_fetch_granularity: int = 0):
         self._lib = _lib.load()
         cfg = GxConfig()
         cfg.abi_version = _lib.GX_ABI_VERSION
@@ -36,6 +37,7 @@ class GraphBuilder:
         cfg.n_ranks = n_ranks
         cfg.expected_kmers = expected_kmers
         cfg.reserved[0] = chunk_bytes
+        cfg.reserved[1] = l2_fetch_granularity or int(os.environ.get("GENOMIX_GB_L2_GRAN", "0"))
         self.kmer_length = kmer_length
         self._ctx = C.c_void_p()
         st = self._lib.gx_create(C.byref(cfg), C.byref(self._ctx))
@@ -84,6 +86,24 @@ class GraphBuilder:
 
     def finish(self) -> None:
         self._check(self._lib.gx_finish(self._ctx))
+
+    # -- multi-GPU exchange (n_ranks > 1) ------------------------------------------------------
+    def mg_unique_id(self) -> np.ndarray:
+        """128-byte NCCL unique id; call on rank 0 and broadcast it to the other ranks."""
+        out = np.zeros(128, dtype=np.uint8)
+        st = self._lib.gx_mg_unique_id(C.c_void_p(out.ctypes.data))
+        if st != 0:
+            raise GenomixError(st, "ncclGetUniqueId failed")
+        return out
+
+    def mg_init(self, unique_id) -> None:
+        uid = np.ascontiguousarray(np.asarray(unique_id, dtype=np.uint8))
+        assert uid.size == 128
+        self._check(self._lib.gx_mg_init(self._ctx, C.c_void_p(uid.ctypes.data)))
+
+    def mg_exchange(self) -> None:
+        """Collective: route staged k-mer and read-head records to their owner GPUs and fold them in."""
+        self._check(self._lib.gx_mg_exchange(self._ctx))
 
     # -- output -----------------------------------------------------------------------------
     @property
