@@ -242,39 +242,41 @@ int alloc_table(gx_ctx* c, u64 capacity, u64** out) {
     return GX_OK;
 }
 
-// make room for `incoming` more occurrences (upper bound on new distinct keys)
-int reserve_table(gx_ctx* c, u64 distinct, u64 incoming) {
-    const u64 need = distinct + incoming;
+// Capacity policy. The table never holds more than GROW_LOAD * capacity keys: before a batch of inserts the
+// host asks for `room` (how many NEW keys may still arrive) and sizes the batch to it, so the bound holds even
+// if every occurrence of the batch is a new key; high-coverage data keeps re-using the same room. The table is
+// doubled (rehash) only when the room drops under capacity/8 or under `min_room`.
+//   distinct : keys in the table now (Counters::distinct after a sync)
+//   hint     : expected number of further occurrences (sizes the very first allocation only)
+int reserve_room(gx_ctx* c, u64 distinct, u64 min_room, u64 hint, u64* room) {
     if (c->table && !c->table_live) {
-        // allocation kept across gx_reset: reuse it if it is big enough, else drop it
-        if ((double)need <= GROW_LOAD * (double)c->capacity) {
-            c->ops->init_table(c->table, c->capacity, c->stream);
-            GX_TRY(check_launch(c, "init_table"));
-            c->table_live = true;
-            return GX_OK;
-        }
-        CUDA_TRY(c, cudaFree(c->table));
-        c->table = nullptr;
-        c->capacity = 0;
+        // allocation kept across gx_reset: re-initialise and reuse (it is grown below if it turns out too small)
+        c->ops->init_table(c->table, c->capacity, c->stream);
+        GX_TRY(check_launch(c, "init_table"));
+        c->table_live = true;
     }
-    if (c->table && (double)need <= GROW_LOAD * (double)c->capacity) return GX_OK;
-    u64 ncap = std::max<u64>(MIN_CAPACITY, (u64)((double)need / TARGET_LOAD) + 1);
-    if (c->table) ncap = std::max<u64>(ncap, c->capacity * 2);
-    if (!c->table && c->cfg.expected_kmers)
-        ncap = std::max<u64>(ncap, (u64)((double)c->cfg.expected_kmers / TARGET_LOAD) + 1);
-    u64* nt = nullptr;
-    GX_TRY(alloc_table(c, ncap, &nt));
-    if (c->table) {
+    if (!c->table) {
+        u64 ncap = std::max<u64>(MIN_CAPACITY, c->cfg.expected_kmers ? (u64)((double)c->cfg.expected_kmers / TARGET_LOAD) + 1
+                                                                     : hint + 1);
+        GX_TRY(alloc_table(c, ncap, &c->table));
+        c->capacity = ncap;
+        c->table_live = true;
+    }
+    for (;;) {
+        const u64 limit = (u64)(GROW_LOAD * (double)c->capacity);
+        const u64 have = limit > distinct ? limit - distinct : 0;
+        if (have >= std::max<u64>(c->capacity / 8, std::max<u64>(min_room, 1))) { *room = have; return GX_OK; }
+        const u64 ncap = c->capacity * 2;
+        u64* nt = nullptr;
+        GX_TRY(alloc_table(c, ncap, &nt));
         c->ops->rehash(c->table, c->capacity, nt, ncap, c->stream);
         GX_TRY(check_launch(c, "rehash"));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
         CUDA_TRY(c, cudaFree(c->table));
         ++c->grows;
+        c->table = nt;
+        c->capacity = ncap;
     }
-    c->table = nt;
-    c->capacity = ncap;
-    c->table_live = true;
-    return GX_OK;
 }
 
 // One chunk of text resident in device memory: line index -> parse -> reserve -> extract+insert.
@@ -317,12 +319,18 @@ int push_chunk_device(gx_ctx* c, const uint8_t* d_text, size_t n) {
     GX_TRY(ensure(c, c->heads, (size_t)h.head_cursor * c->ops->head_bytes,
                   (size_t)(h.head_cursor - h.chunk_reads) * c->ops->head_bytes, true));
     GX_TRY(ensure(c, c->store, (size_t)h.store_cursor, (size_t)(h.store_cursor - h.chunk_store)));
-    GX_TRY(reserve_table(c, h.distinct, h.chunk_occ));
-    {
+    // extract + insert, in as many line ranges as the table's room dictates (usually one)
+    const u64 max_line_occ = std::max<u64>(h.chunk_max_line_occ, 1);
+    u64 distinct = h.distinct, occ_left = h.chunk_occ;
+    for (u64 line0 = 0; line0 < n_lines;) {
+        u64 room = 0;
+        GX_TRY(reserve_room(c, distinct, max_line_occ, h.chunk_occ, &room));
+        u64 take = n_lines - line0;
+        if (occ_left > room) take = std::min<u64>(take, std::max<u64>(room / max_line_occ, 1));
         ScopedPhase ph(c, PH_INSERT);
         ExtractArgs a{};
         a.text = d_text; a.n_text = n;
-        a.desc = (const LineDesc*)c->desc.p; a.n_lines = n_lines;
+        a.desc = (const LineDesc*)c->desc.p + line0; a.n_lines = take;
         a.k = c->k;
         a.table = c->table; a.capacity = c->capacity;
         a.heads = c->heads.p;
@@ -330,12 +338,18 @@ int push_chunk_device(gx_ctx* c, const uint8_t* d_text, size_t n) {
         a.ctr = c->d_ctr;
         a.n_ranks = 1; a.rank = 0;
         if (c->cfg.n_ranks > 1) {
-            GX_TRY(mg_prepare_route(c, h.chunk_occ, a));
+            GX_TRY(mg_prepare_route(c, std::min<u64>(occ_left, take * max_line_occ), a));
             c->ops->extract_route(a, c->stream);
             GX_TRY(check_launch(c, "extract_route"));
         } else {
             c->ops->extract_insert(a, c->stream);
             GX_TRY(check_launch(c, "extract_insert"));
+        }
+        line0 += take;
+        if (line0 < n_lines) {  // more ranges to go: learn how many keys the last one really added
+            GX_TRY(sync_counters(c));
+            distinct = c->h_ctr->distinct;
+            occ_left = occ_left > take ? occ_left - take : 0;  // lower bound of what was consumed: every line has >= 1
         }
     }
     return GX_OK;
@@ -545,7 +559,7 @@ int gx_finish(gx_ctx* c) {
         if (pending) return fail(c, GX_ERR_STATE, "gx_finish: %llu routed records not exchanged yet (call gx_mg_exchange on every rank first)",
                                  (unsigned long long)pending);
     }
-    if (!c->table || !c->table_live) GX_TRY(reserve_table(c, 0, 0));  // empty job: empty table, zero records
+    if (!c->table || !c->table_live) { u64 room; GX_TRY(reserve_room(c, 0, 0, 0, &room)); }  // empty job: empty table, zero records
     const u64 cap = c->capacity;
     const u64 n_heads = c->h_ctr->head_cursor;
     const u64 n_tiles = (cap + EM_TILE - 1) / EM_TILE;

@@ -156,7 +156,8 @@ int gx_mg_exchange(gx_ctx* c) {
     for (int d = 0; d < n; ++d) {
         if (d == me) continue;
         GX_TRY(ensure(c, m->send_heads[d], (size_t)std::max<u64>(new_heads, 1) * c->ops->head_bytes));
-        GX_TRY(ensure(c, m->send_store[d], (size_t)std::max<u64>(new_store, 1)));
+        // both mates of a pair reference the same two packed sequences and may go to the same owner: 2x
+        GX_TRY(ensure(c, m->send_store[d], (size_t)std::max<u64>(2 * new_store, 1)));
     }
     GX_TRY(mg_upload_ptrs(c));
     if (new_heads) {
@@ -187,7 +188,6 @@ int gx_mg_exchange(gx_ctx* c) {
     GX_TRY(ensure(c, m->recv_meta, (size_t)std::max<u64>(recv_kmers, 1) * sizeof(unsigned short)));
     GX_TRY(ensure(c, c->heads, (size_t)(head_cursor + recv_heads) * c->ops->head_bytes, (size_t)head_cursor * c->ops->head_bytes, true));
     GX_TRY(ensure(c, c->store, (size_t)(store_cursor + recv_store), (size_t)store_cursor));
-    GX_TRY(reserve_table(c, c->h_ctr->distinct, recv_kmers));
     // ---- 4. all-to-all-v over NVLink
     NCCL_TRY(c, ncclGroupStart());
     {
@@ -215,9 +215,22 @@ int gx_mg_exchange(gx_ctx* c) {
     }
     NCCL_TRY(c, ncclGroupEnd());
     // ---- 5. fold what arrived
-    c->ops->insert_records((const u64*)m->recv_keys.p, (const unsigned short*)m->recv_meta.p, nullptr, recv_kmers, c->table,
-                           c->capacity, c->d_ctr, c->stream);
-    if (recv_kmers) GX_TRY(check_launch(c, "insert_records"));
+    {
+        u64 distinct = c->h_ctr->distinct;
+        for (u64 done = 0; done < recv_kmers;) {
+            u64 room = 0;
+            GX_TRY(reserve_room(c, distinct, 1, recv_kmers, &room));
+            const u64 take = std::min<u64>(recv_kmers - done, room);
+            c->ops->insert_records((const u64*)m->recv_keys.p + done * c->kw, (const unsigned short*)m->recv_meta.p + done, nullptr,
+                                   take, c->table, c->capacity, c->d_ctr, c->stream);
+            GX_TRY(check_launch(c, "insert_records"));
+            done += take;
+            if (done < recv_kmers) {
+                GX_TRY(sync_counters(c));
+                distinct = c->h_ctr->distinct;
+            }
+        }
+    }
     {
         u64 rh = 0, rs = 0;
         for (int p = 0; p < n; ++p) {

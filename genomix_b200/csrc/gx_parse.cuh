@@ -25,6 +25,7 @@ struct Counters {
     u64 heads_missing;   // internal consistency: heads whose key was not found at finish (must stay 0)
     u64 read_heads;      // ReadHeadInfo entries after de-duplication
     u64 table_overflow;  // upserts that ran out of probe budget (must stay 0)
+    u64 chunk_max_line_occ;  // largest k-mer occurrence count of one line in the current chunk
     u64 scratch[2];
 };
 
@@ -88,6 +89,7 @@ static __global__ void finish_line_index_kernel(const uint8_t* __restrict__ text
     ctr->chunk_reads = 0;
     ctr->chunk_occ = 0;
     ctr->chunk_store = 0;
+    ctr->chunk_max_line_occ = 0;
 }
 
 __device__ __forceinline__ void report_line_error(Counters* ctr, u64 global_line, u32 code) {
@@ -187,6 +189,13 @@ static __global__ void __launch_bounds__(PL_THREADS) parse_lines_kernel(const ui
     }
     const u64 b_sum = block_reduce_sum<PL_THREADS>(bases);
     const u64 o_sum = block_reduce_sum<PL_THREADS>(occ);
+    // per-line maximum: warp reduce, one atomic per warp that has something to report
+    {
+        u64 mx = occ;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        if ((threadIdx.x & 31) == 0 && mx > 0 && mx > ctr->chunk_max_line_occ) atomicMax(&ctr->chunk_max_line_occ, mx);
+    }
     if (threadIdx.x == 0) {
         atomicAdd(&ctr->chunk_reads, tot & 0xfffffull);
         atomicAdd(&ctr->chunk_store, tot >> 20);

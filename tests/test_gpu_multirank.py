@@ -36,4 +36,12 @@ def test_union_of_ranks_equals_oracle(world, tmp_path):
     results = pickle.load(open(outp, "rb"))
     for (k, text), got in zip(cases, results):
         want = gx.types.canonical_records(CO.build_graph_records(k, text, 4)[0])
-        assert got == want
+        if got != want:
+            missing = [key for key in want if key not in got]
+            extra = [key for key in got if key not in want]
+            differ = [key for key in want if key in got and got[key] != want[key]]
+            msg = [f"k={k}: want {len(want)} nodes, got {len(got)}; missing {len(missing)}, extra {len(extra)}, differing {len(differ)}"]
+            for key in differ[:3]:
+                msg.append("want " + str(gx.types.Node.read(want[key], 0)[0]))
+                msg.append("got  " + str(gx.types.Node.read(got[key], 0)[0]))
+            raise AssertionError("\n".join(msg))
