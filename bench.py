@@ -229,12 +229,12 @@ def main():
             gb.mg_exchange()
         gb.finish()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # started before the warm-up so that short timed regions still get samples (all under load)
     for _ in range(args.warmup):
         step_device()
     stats = gb.stats()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = gb.kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     phase_acc = {}

@@ -73,7 +73,7 @@ struct gx_ctx {
 
     DevBuf heads, store;
     DevBuf text, nl_pos, desc, tile_sums;
-    DevBuf hslot, hcount, hstart, hperm, tile_bytes, tile_nodes, records, rec_offsets, parts;
+    DevBuf hslot, hcount, hstart, hperm, tile_bytes, tile_nodes, records, rec_offsets, parts, dense;
 
     u64 global_lines = 0;
     u64 n_nodes = 0, record_bytes = 0;
@@ -458,7 +458,7 @@ void gx_destroy(gx_ctx* c) {
     mg_destroy(c);
     for (auto e : c->event_pool) cudaEventDestroy(e);
     DevBuf* bufs[] = {&c->heads, &c->store, &c->text, &c->nl_pos, &c->desc, &c->tile_sums, &c->hslot, &c->hcount, &c->hstart,
-                      &c->hperm, &c->tile_bytes, &c->tile_nodes, &c->records, &c->rec_offsets, &c->parts};
+                      &c->hperm, &c->tile_bytes, &c->tile_nodes, &c->records, &c->rec_offsets, &c->parts, &c->dense};
     for (auto* b : bufs) release(*b);
     if (c->table) cudaFree(c->table);
     if (c->d_ctr) cudaFree(c->d_ctr);
@@ -623,14 +623,25 @@ int gx_finish(gx_ctx* c) {
     c->n_nodes = c->h_ctr->scratch[1];
     GX_TRY(ensure(c, c->records, (size_t)c->record_bytes + 16));
     GX_TRY(ensure(c, c->rec_offsets, (size_t)(c->n_nodes + 1) * sizeof(u64)));
+    GX_TRY(ensure(c, c->dense, (size_t)std::max<u64>(c->n_nodes, 1) * (c->kw + 2) * sizeof(u64)));
     a.out = (uint8_t*)c->records.p;
     a.rec_offsets = (u64*)c->rec_offsets.p;
+    a.dense = (u64*)c->dense.p;
+    a.n_nodes = c->n_nodes;
+    {
+        // staging area: 1.5x the average bytes of EM_THREADS nodes; the rare CTA that needs more writes directly
+        const u64 avg = c->n_nodes ? c->record_bytes / c->n_nodes + 1 : 64;
+        u64 stage = (avg * EM_THREADS * 3 / 2 + 2048 + 15) & ~15ull;
+        a.stage_bytes = (u32)std::min<u64>(std::max<u64>(stage, 8192), EM_MAX_STAGE_BYTES);
+    }
     {
         ScopedPhase ph(c, PH_FINISH);
-        c->ops->emit_serialise(a, c->stream);
-        GX_TRY(check_launch(c, "emit_serialise"));
         CUDA_TRY(c, cudaMemcpyAsync((u64*)c->rec_offsets.p + c->n_nodes, &c->h_ctr->scratch[0], sizeof(u64),
                                     cudaMemcpyHostToDevice, c->stream));
+        c->ops->emit_compact(a, c->stream);
+        GX_TRY(check_launch(c, "emit_compact"));
+        c->ops->emit_serialise(a, c->stream);
+        if (c->n_nodes) GX_TRY(check_launch(c, "emit_serialise"));
     }
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     drain_timers(c);

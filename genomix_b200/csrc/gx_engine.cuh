@@ -483,8 +483,7 @@ static __global__ void bump_cursors_kernel(Counters* ctr, u64 heads, u64 store_b
 static constexpr int EM_THREADS = 256;
 static constexpr int EM_PER_THREAD = 4;
 static constexpr int EM_TILE = EM_THREADS * EM_PER_THREAD;  // slots per tile (CTA)
-static constexpr int EM_STAGE_BYTES = 60 * 1024;             // shared-memory staging of a tile's records
-static constexpr int EM_SMEM_BYTES = EM_STAGE_BYTES + 16 + EM_TILE * 12;
+static constexpr int EM_MAX_STAGE_BYTES = 160 * 1024;        // upper bound of the serialise kernel's staging area
 
 struct EmitArgs {
     const u64* table; u64 capacity; int k;
@@ -492,6 +491,8 @@ struct EmitArgs {
     const uint8_t* store;
     u64* tile_bytes; u64* tile_nodes;   // per tile: sums (size pass) then exclusive bases (after the scan)
     uint8_t* out; u64* rec_offsets;
+    u64* dense; u64 n_nodes;            // dense node list: (KW key words, value word, slot) per node, slot order
+    u32 stage_bytes;                    // dynamic shared memory staging area of the serialise kernel
 };
 
 __device__ __forceinline__ u32 head_bytes(u32 this_len, u32 mate_len) {
@@ -614,13 +615,9 @@ __device__ __forceinline__ void put_kmer_bytes(WordWriter& w, const u64 (&x)[KW]
 // Node.write (Node.java:408-427) + getActiveFields (:466-487) behind the SequenceFile record framing
 // (recordLength, keyLength, VKmer.write VKmer.java:389-391).
 template <int KW>
-__device__ void serialise_node(const EmitArgs& a, u64 slot, const u64* __restrict__ s, u32 rec_bytes, u32 n_unflipped,
+__device__ void serialise_node(const EmitArgs& a, u64 slot, const u64 (&key)[KW], u64 val, u32 rec_bytes, u32 n_unflipped,
                                u32 n_flipped, uint8_t* dst) {
     const u32 nb = (u32)(a.k + 3) / 4u;
-    u64 key[KW];
-#pragma unroll
-    for (int j = 0; j < KW; ++j) key[j] = s[j];
-    const u64 val = s[KW];
     const u32 mask = (u32)(val >> MASK_SHIFT);
     const u64 count = val & COUNT_MASK;
     WordWriter w;
@@ -636,14 +633,23 @@ __device__ void serialise_node(const EmitArgs& a, u64 slot, const u64* __restric
     if (n_unflipped) active |= 1u << 4;
     if (n_flipped) active |= 1u << 5;
     w.put8(active);
+    // all 16 possible neighbours are one-letter shifts of X or of rc(X) (gx_internal.cuh header):
+    //   FF b: X[1:]+b   FR b: rc(X[1:]+b) = (3-b)+rc(X)[:-1]   RF b: rc(b+X[:-1]) = rc(X)[1:]+(3-b)   RR b: b+X[:-1]
+    u64 rcx[KW];
+    revcomp_key<KW>(key, a.k, rcx);
+#pragma unroll
     for (int t = 0; t < 4; ++t) {
         const u32 bits = (mask >> (4 * t)) & 0xfu;
         if (!bits) continue;
         w.put32be((u32)__popc(bits));
+#pragma unroll
         for (u32 b = 0; b < 4; ++b) {
             if (!((bits >> b) & 1u)) continue;
             u64 nk[KW];
-            neighbour_key<KW>(key, a.k, t, b, nk);
+            if (t == 0) key_append<KW>(key, a.k, b, nk);
+            else if (t == 1) key_prepend<KW>(rcx, a.k, 3u - b, nk);
+            else if (t == 2) key_append<KW>(rcx, a.k, 3u - b, nk);
+            else key_prepend<KW>(key, a.k, b, nk);
             w.put32be((u32)a.k);
             put_kmer_bytes<KW>(w, nk, nb);
         }
@@ -676,58 +682,70 @@ __device__ void serialise_node(const EmitArgs& a, u64 slot, const u64* __restric
     w.finish();
 }
 
-// Phase 1: every thread sizes its 4 slots, a block scan turns sizes into byte offsets and node ranks, and the
-// occupied slots are written to a dense shared-memory work list. Phase 2: threads take nodes from the dense
-// list (full warps instead of one live lane in three) and serialise into the staging area, which the CTA then
-// copies out with aligned 16-byte stores.
+// Pass 2 (after the tile sums are scanned): compact the occupied slots into a dense node list in slot order and
+// give every node its byte offset in the record stream. Streaming, every lane busy.
 template <int KW>
-__global__ void __launch_bounds__(EM_THREADS) emit_serialise_kernel(EmitArgs a) {
+__global__ void __launch_bounds__(EM_THREADS) emit_compact_kernel(EmitArgs a) {
     constexpr int SW = SlotTraits<KW>::WORDS;
-    extern __shared__ __align__(16) uint8_t smem_dyn[];
-    uint2* work = reinterpret_cast<uint2*>(smem_dyn);                 // [EM_TILE] (local slot | nu<<12 | nf<<22, byte offset)
-    u32* work_sz = reinterpret_cast<u32*>(smem_dyn + EM_TILE * 8);    // [EM_TILE] record bytes
-    uint8_t* stage = smem_dyn + EM_TILE * 12;
-    const u64 tile0 = (u64)blockIdx.x * EM_TILE;
-    const u32 local0 = threadIdx.x * EM_PER_THREAD;
-    u32 sz[EM_PER_THREAD], nu[EM_PER_THREAD], nf[EM_PER_THREAD];
+    constexpr int DW = KW + 2;
+    const u64 tile0 = (u64)blockIdx.x * EM_TILE + (u64)threadIdx.x * EM_PER_THREAD;
+    u32 sz[EM_PER_THREAD];
     u32 my_bytes = 0, my_nodes = 0;
 #pragma unroll
     for (int i = 0; i < EM_PER_THREAD; ++i) {
-        sz[i] = nu[i] = nf[i] = 0;
-        const u64 slot = tile0 + local0 + i;
+        sz[i] = 0;
+        const u64 slot = tile0 + i;
         if (slot < a.capacity) {
             const u64* s = a.table + slot * SW;
-            if (slot_occupied<KW>(s)) sz[i] = node_record_bytes<KW>(a, slot, s[KW], nu[i], nf[i]);
+            u32 nu, nf;
+            if (slot_occupied<KW>(s)) sz[i] = node_record_bytes<KW>(a, slot, s[KW], nu, nf);
         }
         my_bytes += sz[i];
         my_nodes += sz[i] ? 1u : 0u;
     }
     u64 tile_total, tile_nodes;
-    u64 ex = block_scan_excl<EM_THREADS>((u64)my_bytes, &tile_total);
-    u64 nex = block_scan_excl<EM_THREADS>((u64)my_nodes, &tile_nodes);
-    const u64 gbase = a.tile_bytes[blockIdx.x];
-    const u64 nbase = a.tile_nodes[blockIdx.x];
+    u64 ex = a.tile_bytes[blockIdx.x] + block_scan_excl<EM_THREADS>((u64)my_bytes, &tile_total);
+    u64 nex = a.tile_nodes[blockIdx.x] + block_scan_excl<EM_THREADS>((u64)my_nodes, &tile_nodes);
 #pragma unroll
     for (int i = 0; i < EM_PER_THREAD; ++i) {
         if (!sz[i]) continue;
-        a.rec_offsets[nbase + nex] = gbase + ex;
-        // nu/nf only steer the head loops; they are re-derived exactly in phase 2 when they do not fit
-        work[nex] = make_uint2((local0 + i) | (min(nu[i], 1023u) << 12) | (min(nf[i], 1023u) << 22), (u32)ex);
-        work_sz[nex] = sz[i];
+        const u64 slot = tile0 + i;
+        const u64* s = a.table + slot * SW;
+        u64* d = a.dense + nex * DW;
+#pragma unroll
+        for (int j = 0; j <= KW; ++j) d[j] = s[j];  // key words and the value word
+        d[KW + 1] = slot;
+        a.rec_offsets[nex] = ex;
         ex += sz[i];
         ++nex;
     }
+}
+
+// Pass 3: one thread per node of the dense list; a CTA's EM_THREADS consecutive nodes cover one contiguous byte
+// range of the stream, staged in shared memory and copied out with aligned 16-byte stores.
+template <int KW>
+__global__ void __launch_bounds__(EM_THREADS) emit_serialise_kernel(EmitArgs a) {
+    constexpr int DW = KW + 2;
+    extern __shared__ __align__(16) uint8_t stage[];
+    const u64 n0 = (u64)blockIdx.x * EM_THREADS;
+    const u64 n1 = min(n0 + (u64)EM_THREADS, a.n_nodes);
+    const u64 gbase = a.rec_offsets[n0];
+    const u64 tile_total = a.rec_offsets[n1] - gbase;  // rec_offsets[n_nodes] = total bytes
     const u32 skew = (u32)(((uintptr_t)(a.out + gbase)) & 15u);
-    const bool staged = tile_total + skew <= (u64)EM_STAGE_BYTES;
-    __syncthreads();
-    for (u32 n = threadIdx.x; n < (u32)tile_nodes; n += EM_THREADS) {
-        const uint2 wk = work[n];
-        const u64 slot = tile0 + (wk.x & 0xfffu);
-        u32 cu = (wk.x >> 12) & 0x3ffu, cf = (wk.x >> 22) & 0x3ffu;
-        const u64* s = a.table + slot * SW;
-        if (cu == 1023u || cf == 1023u) (void)node_record_bytes<KW>(a, slot, s[KW], cu, cf);
-        uint8_t* dst = staged ? (stage + skew + wk.y) : (a.out + gbase + wk.y);
-        serialise_node<KW>(a, slot, s, work_sz[n], cu, cf, dst);
+    const bool staged = tile_total + skew <= (u64)a.stage_bytes;
+    const u64 n = n0 + threadIdx.x;
+    if (n < n1) {
+        const u64* d = a.dense + n * DW;
+        u64 key[KW];
+#pragma unroll
+        for (int j = 0; j < KW; ++j) key[j] = d[j];
+        const u64 val = d[KW], slot = d[KW + 1];
+        const u64 off = a.rec_offsets[n];
+        const u32 sz = (u32)(a.rec_offsets[n + 1] - off);
+        u32 nu = 0, nf = 0;
+        if (a.hcount && a.hcount[slot]) (void)node_record_bytes<KW>(a, slot, val, nu, nf);
+        uint8_t* dst = staged ? (stage + skew + (off - gbase)) : (a.out + off);
+        serialise_node<KW>(a, slot, key, val, sz, nu, nf, dst);
     }
     if (!staged) return;
     __syncthreads();
@@ -775,6 +793,7 @@ struct EngineOps {
     void (*heads_sort)(const void* heads, const u64* hslot, u64 n_heads, u64 capacity, const u32* hstart, u32* hcount,
                        u32* hperm, Counters* ctr, cudaStream_t st);
     void (*emit_size)(const EmitArgs& a, cudaStream_t st);
+    void (*emit_compact)(const EmitArgs& a, cudaStream_t st);
     void (*emit_serialise)(const EmitArgs& a, cudaStream_t st);
     void (*route_heads)(const HeadRouteArgs& a, cudaStream_t st);
     void (*rebase_heads)(void* heads, u64 first, u64 n, u64 store_base, cudaStream_t st);

@@ -147,7 +147,9 @@ __host__ __device__ __forceinline__ void key_append(const u64 (&x)[KW], int k, u
         y[i] = lo | hi;
     }
     const int pos = 2 * (k - 1);
-    y[pos >> 6] |= (u64)base << (pos & 63);
+#pragma unroll
+    for (int i = 0; i < KW; ++i)  // static indices keep y[] in registers
+        if (i == (pos >> 6)) y[i] |= (u64)base << (pos & 63);
 }
 
 // Y = base + X[:-1]  (prepend at position 0, drop letter k-1)

@@ -37,8 +37,12 @@ void l_heads_sort(const void* heads, const u64* hslot, u64 n_heads, u64 capacity
 void l_emit_size(const EmitArgs& a, cudaStream_t st) {
     emit_size_kernel<KW><<<(unsigned)((a.capacity + EM_TILE - 1) / EM_TILE), EM_THREADS, 0, st>>>(a);
 }
+void l_emit_compact(const EmitArgs& a, cudaStream_t st) {
+    emit_compact_kernel<KW><<<(unsigned)((a.capacity + EM_TILE - 1) / EM_TILE), EM_THREADS, 0, st>>>(a);
+}
 void l_emit_serialise(const EmitArgs& a, cudaStream_t st) {
-    emit_serialise_kernel<KW><<<(unsigned)((a.capacity + EM_TILE - 1) / EM_TILE), EM_THREADS, EM_SMEM_BYTES, st>>>(a);
+    if (a.n_nodes == 0) return;
+    emit_serialise_kernel<KW><<<(unsigned)((a.n_nodes + EM_THREADS - 1) / EM_THREADS), EM_THREADS, a.stage_bytes, st>>>(a);
 }
 void l_route_heads(const HeadRouteArgs& a, cudaStream_t st) {
     if (a.n == 0) return;
@@ -49,7 +53,7 @@ void l_rebase_heads(void* heads, u64 first, u64 n, u64 store_base, cudaStream_t 
     rebase_heads_kernel<KW><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(heads, first, n, store_base);
 }
 int l_prepare() {
-    return (int)cudaFuncSetAttribute(emit_serialise_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, EM_SMEM_BYTES);
+    return (int)cudaFuncSetAttribute(emit_serialise_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, EM_MAX_STAGE_BYTES);
 }
 
 const EngineOps OPS = {KW,
@@ -63,6 +67,7 @@ const EngineOps OPS = {KW,
                        l_heads_count,
                        l_heads_sort,
                        l_emit_size,
+                       l_emit_compact,
                        l_emit_serialise,
                        l_route_heads,
                        l_rebase_heads,
