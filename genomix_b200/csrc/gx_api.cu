@@ -39,6 +39,8 @@ constexpr double GROW_LOAD = 0.70;    // never let distinct + incoming exceed th
 constexpr double TARGET_LOAD = 0.50;  // capacity chosen for this load
 constexpr u64 MIN_CAPACITY = 1ull << 16;
 constexpr size_t DEFAULT_CHUNK = 64ull << 20;
+constexpr size_t REGION_BYTES = 32ull << 20;            // table region kept L2-resident by the blocked build
+constexpr size_t BLOCKED_MIN_TABLE_BYTES = 192ull << 20;  // smaller tables are L2-friendly enough for the direct build
 
 struct DevBuf {
     void* p = nullptr;
@@ -74,6 +76,9 @@ struct gx_ctx {
     DevBuf heads, store;
     DevBuf text, nl_pos, desc, tile_sums;
     DevBuf hslot, hcount, hstart, hperm, tile_bytes, tile_nodes, records, rec_offsets, parts, dense;
+    DevBuf flat_keys, flat_meta, part_keys, part_meta, bucket_count;  // L2-blocked build
+    int blocked_mode = 0;      // 0 auto, 1 never, 2 always (cfg.reserved[2]; tests and A/B runs)
+    u32 blocked_buckets = 0;   // 0 auto (cfg.reserved[3])
 
     u64 global_lines = 0;
     u64 n_nodes = 0, record_bytes = 0;
@@ -279,6 +284,81 @@ int reserve_room(gx_ctx* c, u64 distinct, u64 min_room, u64 hint, u64* room) {
     }
 }
 
+// Insert `n` (key, mask) records that are already grouped by table region (bucket b = records
+// [offsets[b], offsets[b+1])), one launch per region, in groups of regions that fit the table's room.
+int blocked_insert(gx_ctx* c, const u64* keys, const unsigned short* meta, const std::vector<u64>& offsets, u64 distinct) {
+    const u32 n_buckets = (u32)offsets.size() - 1;
+    u64 max_bucket = 1;
+    for (u32 b = 0; b < n_buckets; ++b) max_bucket = std::max<u64>(max_bucket, offsets[b + 1] - offsets[b]);
+    for (u32 b = 0; b < n_buckets;) {
+        u64 room = 0;
+        GX_TRY(reserve_room(c, distinct, max_bucket, offsets[n_buckets], &room));
+        u32 e = b;
+        u64 group = 0;
+        while (e < n_buckets && (e == b || group + (offsets[e + 1] - offsets[e]) <= room)) { group += offsets[e + 1] - offsets[e]; ++e; }
+        {
+            ScopedPhase ph(c, PH_INSERT);
+            for (u32 i = b; i < e; ++i) {
+                const u64 cnt = offsets[i + 1] - offsets[i];
+                if (!cnt) continue;
+                c->ops->insert_records(keys + offsets[i] * c->kw, meta + offsets[i], nullptr, cnt, c->table, c->capacity, c->d_ctr,
+                                       c->stream);
+                GX_TRY(check_launch(c, "insert_records"));
+            }
+        }
+        b = e;
+        if (b < n_buckets) {
+            GX_TRY(sync_counters(c));
+            distinct = c->h_ctr->distinct;
+        }
+    }
+    return GX_OK;
+}
+
+// L2-blocked handling of one parsed chunk: pass 1 extract_kernel<EX_FLAT>, pass 2
+// partition_flat_kernel, pass 3 blocked_insert.
+int blocked_chunk(gx_ctx* c, const uint8_t* d_text, size_t n, u64 n_lines, u64 chunk_occ, u32 n_buckets, u64 distinct) {
+    GX_TRY(ensure(c, c->flat_keys, (size_t)chunk_occ * c->kw * sizeof(u64)));
+    GX_TRY(ensure(c, c->flat_meta, (size_t)chunk_occ * sizeof(unsigned short)));
+    GX_TRY(ensure(c, c->part_keys, (size_t)chunk_occ * c->kw * sizeof(u64)));
+    GX_TRY(ensure(c, c->part_meta, (size_t)chunk_occ * sizeof(unsigned short)));
+    GX_TRY(ensure(c, c->bucket_count, (size_t)MAX_BUCKETS * sizeof(u64)));
+    std::vector<u64> counts(n_buckets), offsets(n_buckets + 1, 0);
+    {
+        ScopedPhase ph(c, PH_INSERT);
+        CUDA_TRY(c, cudaMemsetAsync(c->bucket_count.p, 0, (size_t)n_buckets * sizeof(u64), c->stream));
+        ExtractArgs a{};
+        a.text = d_text; a.n_text = n;
+        a.desc = (const LineDesc*)c->desc.p; a.n_lines = n_lines;
+        a.k = c->k;
+        a.table = c->table; a.capacity = c->capacity;
+        a.heads = c->heads.p;
+        a.store = (uint8_t*)c->store.p;
+        a.ctr = c->d_ctr;
+        a.n_ranks = 1; a.rank = 0;
+        a.flat_keys = (u64*)c->flat_keys.p; a.flat_meta = (unsigned short*)c->flat_meta.p;
+        a.bucket_count = (u64*)c->bucket_count.p; a.n_buckets = n_buckets;
+        c->ops->extract_flat(a, c->stream);
+        GX_TRY(check_launch(c, "extract_flat"));
+        CUDA_TRY(c, cudaMemcpyAsync(counts.data(), c->bucket_count.p, (size_t)n_buckets * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    drain_timers(c);
+    for (u32 b = 0; b < n_buckets; ++b) offsets[b + 1] = offsets[b] + counts[b];
+    if (offsets[n_buckets] != chunk_occ)
+        return c->sticky = fail(c, GX_ERR_INVALID, "internal error: flat extract produced %llu of %llu occurrences",
+                                (unsigned long long)offsets[n_buckets], (unsigned long long)chunk_occ);
+    {
+        ScopedPhase ph(c, PH_INSERT);
+        CUDA_TRY(c, cudaMemcpyAsync(c->bucket_count.p, offsets.data(), (size_t)n_buckets * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+        c->ops->partition_flat((const u64*)c->flat_keys.p, (const unsigned short*)c->flat_meta.p, chunk_occ, n_buckets,
+                               (u64*)c->bucket_count.p, (u64*)c->part_keys.p, (unsigned short*)c->part_meta.p, c->stream);
+        GX_TRY(check_launch(c, "partition_flat"));
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // offsets (pageable) were the source of an async copy
+    return blocked_insert(c, (const u64*)c->part_keys.p, (const unsigned short*)c->part_meta.p, offsets, distinct);
+}
+
 // One chunk of text resident in device memory: line index -> parse -> reserve -> extract+insert.
 int push_chunk_device(gx_ctx* c, const uint8_t* d_text, size_t n) {
     if (n == 0) return GX_OK;
@@ -319,9 +399,23 @@ int push_chunk_device(gx_ctx* c, const uint8_t* d_text, size_t n) {
     GX_TRY(ensure(c, c->heads, (size_t)h.head_cursor * c->ops->head_bytes,
                   (size_t)(h.head_cursor - h.chunk_reads) * c->ops->head_bytes, true));
     GX_TRY(ensure(c, c->store, (size_t)h.store_cursor, (size_t)(h.store_cursor - h.chunk_store)));
-    // extract + insert, in as many line ranges as the table's room dictates (usually one)
     const u64 max_line_occ = std::max<u64>(h.chunk_max_line_occ, 1);
     u64 distinct = h.distinct, occ_left = h.chunk_occ;
+    // ---- L2-blocked build (single GPU, table much larger than L2): flat extract -> partition by table region ->
+    //      region-by-region insert, so that every table access of the insert is an L2 hit
+    if (c->cfg.n_ranks == 1 && c->blocked_mode != 1) {
+        u64 room = 0;
+        GX_TRY(reserve_room(c, distinct, max_line_occ, h.chunk_occ, &room));
+        const size_t table_bytes = (size_t)c->capacity * c->ops->slot_bytes;
+        // measured on B200 (profiles/r01g): the generic partition pass costs what the random HBM accesses cost, so the
+        // blocked build is opt-in (cfg.reserved[2] == 2) until its partition is fused into the extract kernel
+        if (c->blocked_mode == 2 || (c->blocked_mode == 3 && table_bytes >= BLOCKED_MIN_TABLE_BYTES)) {
+            const u32 n_buckets = c->blocked_buckets ? c->blocked_buckets
+                : (u32)std::min<size_t>(MAX_BUCKETS, std::max<size_t>(2, (table_bytes + REGION_BYTES - 1) / REGION_BYTES));
+            return blocked_chunk(c, d_text, n, n_lines, h.chunk_occ, n_buckets, distinct);
+        }
+    }
+    // ---- direct build: extract + upsert, in as many line ranges as the table's room dictates (usually one)
     for (u64 line0 = 0; line0 < n_lines;) {
         u64 room = 0;
         GX_TRY(reserve_room(c, distinct, max_line_occ, h.chunk_occ, &room));
@@ -410,6 +504,8 @@ int gx_create(const gx_config* cfg, gx_ctx** out) {
     c->kw = (c->k + 31) / 32;
     c->ops = engine_ops(c->kw);
     if (cfg->reserved[0]) c->chunk_bytes = (size_t)cfg->reserved[0];
+    c->blocked_mode = (int)cfg->reserved[2];
+    c->blocked_buckets = (u32)std::min<u64>(cfg->reserved[3], MAX_BUCKETS);
     // tuning knob: L2 fetch granularity in bytes (32/64/128); random 16-32 B slot accesses want the smallest
     if (cfg->reserved[1]) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)cfg->reserved[1]);
     auto bail = [&](int code) { g_create_error = c->err; gx_destroy(c); return code; };
@@ -458,7 +554,8 @@ void gx_destroy(gx_ctx* c) {
     mg_destroy(c);
     for (auto e : c->event_pool) cudaEventDestroy(e);
     DevBuf* bufs[] = {&c->heads, &c->store, &c->text, &c->nl_pos, &c->desc, &c->tile_sums, &c->hslot, &c->hcount, &c->hstart,
-                      &c->hperm, &c->tile_bytes, &c->tile_nodes, &c->records, &c->rec_offsets, &c->parts, &c->dense};
+                      &c->hperm, &c->tile_bytes, &c->tile_nodes, &c->records, &c->rec_offsets, &c->parts, &c->dense,
+                      &c->flat_keys, &c->flat_meta, &c->part_keys, &c->part_meta, &c->bucket_count};
     for (auto* b : bufs) release(*b);
     if (c->table) cudaFree(c->table);
     if (c->d_ctr) cudaFree(c->d_ctr);

@@ -26,6 +26,16 @@ static constexpr int WIN_POSITIONS = 4 * WIN_BYTES - 160;   // k-mer start posit
 #define GX_EX_MIN_BLOCKS 4
 #endif
 static constexpr int EX_BATCH = GX_EX_BATCH;                // groups of 30 positions in flight per warp
+static constexpr int MAX_BUCKETS = 1024;                    // table regions of the L2-blocked build
+
+// Region (bucket) of a key: regions are contiguous slot ranges because slot_of() is monotone in the hash too.
+__host__ __device__ __forceinline__ u32 bucket_of(u64 h, u32 n_buckets) {
+#ifdef __CUDA_ARCH__
+    return (u32)__umul64hi(h, (u64)n_buckets);
+#else
+    return (u32)(((unsigned __int128)h * n_buckets) >> 64);
+#endif
+}
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -42,6 +52,9 @@ struct ExtractArgs {
     u64* const* route_keys;             // [n_ranks] -> send bucket of key words (KW per record)
     unsigned short* const* route_meta;  // [n_ranks] -> send bucket of edge masks
     u64* route_count;                   // [n_ranks] records appended so far
+    // L2-blocked build (EX_FLAT)
+    u64* flat_keys; unsigned short* flat_meta;  // [chunk occurrences] in parse order
+    u64* bucket_count; u32 n_buckets;           // records per table region
 };
 
 // four text bytes at the 4-byte aligned address `w` -> one packed quad; bytes outside [lo, hi) read as 'A'
@@ -122,12 +135,21 @@ __device__ __forceinline__ u32 edge_bit_prev(bool cur_rev, bool prev_rev, u32 a)
 // folded straight into the table (ROUTE == false) or appended to its owner GPU's bucket (ROUTE == true).
 // One warp per input line; lanes 1..30 own consecutive positions, lanes 0 and 31 are halo lanes that
 // only compute the direction of the neighbouring position.
-template <int KW, bool ROUTE>
+enum ExtractMode { EX_UPSERT = 0, EX_ROUTE = 1, EX_FLAT = 2 };
+
+template <int KW, int MODE>
 __global__ void __launch_bounds__(EX_THREADS, GX_EX_MIN_BLOCKS) extract_kernel(ExtractArgs a) {
+    constexpr bool ROUTE = MODE == EX_ROUTE;
+    constexpr bool FLAT = MODE == EX_FLAT;
     __shared__ u64 sq[EX_WARPS][WIN_WORDS];
     // per-lane private stash of a batch's keys and masks (lane-major: conflict-free)
-    __shared__ u64 stash_k[(!ROUTE && EX_BATCH > 1) ? EX_WARPS : 1][EX_BATCH][KW][32];
-    __shared__ unsigned short stash_m[(!ROUTE && EX_BATCH > 1) ? EX_WARPS : 1][EX_BATCH][32];
+    __shared__ u64 stash_k[(MODE == EX_UPSERT && EX_BATCH > 1) ? EX_WARPS : 1][EX_BATCH][KW][32];
+    __shared__ unsigned short stash_m[(MODE == EX_UPSERT && EX_BATCH > 1) ? EX_WARPS : 1][EX_BATCH][32];
+    __shared__ u32 bucket_hist[FLAT ? MAX_BUCKETS : 1];  // this CTA's records per table region (EX_FLAT)
+    if constexpr (FLAT) {
+        for (u32 i = threadIdx.x; i < a.n_buckets; i += EX_THREADS) bucket_hist[i] = 0;
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u64* W = sq[warp];
     uint8_t* Wb = reinterpret_cast<uint8_t*>(W);
@@ -204,7 +226,15 @@ __global__ void __launch_bounds__(EX_THREADS, GX_EX_MIN_BLOCKS) extract_kernel(E
                                 h.flipped = rev ? 1u : 0u;
                                 h.valid = 1u;
                             }
-                            if constexpr (!ROUTE) {
+                            if constexpr (FLAT) {
+                                // L2-blocked build, pass 1: the occurrence goes to its flat slot (no atomics: the parser
+                                // reserved [occ_base, occ_base + positions) for this line) and its table region is counted
+                                const u64 idx = d.occ_base + (mate && (d.flags & 1u) ? (u64)(d.len[0] - (u32)k + 1u) : 0ull) + (u64)p;
+#pragma unroll
+                                for (int i = 0; i < KW; ++i) a.flat_keys[idx * KW + i] = key[i];
+                                a.flat_meta[idx] = (unsigned short)mask;
+                                atomicAdd(&bucket_hist[bucket_of(hash_key<KW>(key), a.n_buckets)], 1u);
+                            } else if constexpr (!ROUTE) {
                                 if constexpr (EX_BATCH == 1) {
                                     bool is_new;
                                     if (table_upsert<KW>(a.table, a.capacity, key, 1ull, mask, is_new) == a.capacity)
@@ -252,7 +282,7 @@ __global__ void __launch_bounds__(EX_THREADS, GX_EX_MIN_BLOCKS) extract_kernel(E
                             }
                         }
                     }
-                    if constexpr (!ROUTE && EX_BATCH > 1) {
+                    if constexpr (MODE == EX_UPSERT && EX_BATCH > 1) {
 #pragma unroll
                         for (int j = 0; j < EX_BATCH; ++j) {
                             if (!((acts >> j) & 1u)) continue;
@@ -272,6 +302,11 @@ __global__ void __launch_bounds__(EX_THREADS, GX_EX_MIN_BLOCKS) extract_kernel(E
 #pragma unroll
     for (int dlt = 16; dlt > 0; dlt >>= 1) new_slots += __shfl_xor_sync(0xffffffffu, new_slots, dlt);
     if (lane == 0 && new_slots) atomicAdd(&a.ctr->distinct, (u64)new_slots);
+    if constexpr (FLAT) {
+        __syncthreads();
+        for (u32 i = threadIdx.x; i < a.n_buckets; i += EX_THREADS)
+            if (bucket_hist[i]) atomicAdd(a.bucket_count + i, (u64)bucket_hist[i]);
+    }
 }
 
 // K2x: upsert pre-extracted (key, mask, count) records (received from other GPUs, or partial aggregates).
@@ -293,6 +328,49 @@ __global__ void __launch_bounds__(256) insert_records_kernel(const u64* __restri
 #pragma unroll
     for (int dlt = 16; dlt > 0; dlt >>= 1) new_slots += __shfl_xor_sync(0xffffffffu, new_slots, dlt);
     if ((threadIdx.x & 31) == 0 && new_slots) atomicAdd(&ctr->distinct, (u64)new_slots);
+}
+
+// L2-blocked build, pass 2: scatter the flat (key, mask) records into per-region segments whose exact
+// offsets come from the histogram taken in pass 1 (bucket_cursor starts at the segment offsets).
+static constexpr int PT_THREADS = 256;
+static constexpr int PT_ITEMS = 8;
+template <int KW>
+__global__ void __launch_bounds__(PT_THREADS) partition_flat_kernel(const u64* __restrict__ flat_keys,
+                                                                    const unsigned short* __restrict__ flat_meta, u64 n,
+                                                                    u32 n_buckets, u64* __restrict__ bucket_cursor,
+                                                                    u64* __restrict__ out_keys,
+                                                                    unsigned short* __restrict__ out_meta) {
+    __shared__ u32 hist[MAX_BUCKETS];
+    __shared__ u64 base[MAX_BUCKETS];
+    for (u32 i = threadIdx.x; i < n_buckets; i += PT_THREADS) hist[i] = 0;
+    __syncthreads();
+    const u64 tile0 = (u64)blockIdx.x * (PT_THREADS * PT_ITEMS);
+    u64 key[PT_ITEMS][KW];
+    u32 bucket[PT_ITEMS], rank[PT_ITEMS];
+#pragma unroll
+    for (int it = 0; it < PT_ITEMS; ++it) {
+        const u64 i = tile0 + (u64)it * PT_THREADS + threadIdx.x;
+        bucket[it] = 0xffffffffu;
+        if (i < n) {
+#pragma unroll
+            for (int j = 0; j < KW; ++j) key[it][j] = __ldcs(flat_keys + i * KW + j);
+            bucket[it] = bucket_of(hash_key<KW>(key[it]), n_buckets);
+            rank[it] = atomicAdd(&hist[bucket[it]], 1u);
+        }
+    }
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < n_buckets; i += PT_THREADS)
+        base[i] = hist[i] ? atomicAdd(bucket_cursor + i, (u64)hist[i]) : 0ull;
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < PT_ITEMS; ++it) {
+        if (bucket[it] == 0xffffffffu) continue;
+        const u64 i = tile0 + (u64)it * PT_THREADS + threadIdx.x;
+        const u64 o = base[bucket[it]] + rank[it];
+#pragma unroll
+        for (int j = 0; j < KW; ++j) out_keys[o * KW + j] = key[it][j];
+        out_meta[o] = __ldcs(flat_meta + i);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -785,6 +863,9 @@ struct EngineOps {
     void (*init_table)(u64* table, u64 capacity, cudaStream_t st);
     void (*extract_insert)(const ExtractArgs& a, cudaStream_t st);
     void (*extract_route)(const ExtractArgs& a, cudaStream_t st);
+    void (*extract_flat)(const ExtractArgs& a, cudaStream_t st);
+    void (*partition_flat)(const u64* flat_keys, const unsigned short* flat_meta, u64 n, u32 n_buckets, u64* bucket_cursor,
+                           u64* out_keys, unsigned short* out_meta, cudaStream_t st);
     void (*insert_records)(const u64* keys, const unsigned short* meta, const u32* counts, u64 n, u64* table,
                            u64 capacity, Counters* ctr, cudaStream_t st);
     void (*rehash)(const u64* old_table, u64 old_capacity, u64* table, u64 capacity, cudaStream_t st);

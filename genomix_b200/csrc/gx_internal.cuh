@@ -40,6 +40,7 @@ struct LineDesc {
     u64 head_idx[2]; // global index into the heads array for each split mate (valid only if flag set)
     u32 flags;       // bit0/bit1: mate 0/1 passes [ACGTacgt]+ (is split); bit2: line has 3 fields
     u32 pad;
+    u64 occ_base;    // chunk-relative index of this line's first k-mer occurrence (mate 0 first, then mate 1)
 };
 
 // One ReadHeadInfo to be (ReadHeadInfo.java:17-28): lives until emit.

@@ -9,10 +9,19 @@ void l_init_table(u64* table, u64 capacity, cudaStream_t st) {
     init_table_kernel<KW><<<grid_for(capacity * SlotTraits<KW>::WORDS, 256, 148 * 32), 256, 0, st>>>(table, capacity);
 }
 void l_extract_insert(const ExtractArgs& a, cudaStream_t st) {
-    extract_kernel<KW, false><<<grid_for(a.n_lines, EX_WARPS, 148 * 8), EX_THREADS, 0, st>>>(a);
+    extract_kernel<KW, EX_UPSERT><<<grid_for(a.n_lines, EX_WARPS, 148 * 8), EX_THREADS, 0, st>>>(a);
 }
 void l_extract_route(const ExtractArgs& a, cudaStream_t st) {
-    extract_kernel<KW, true><<<grid_for(a.n_lines, EX_WARPS, 148 * 8), EX_THREADS, 0, st>>>(a);
+    extract_kernel<KW, EX_ROUTE><<<grid_for(a.n_lines, EX_WARPS, 148 * 8), EX_THREADS, 0, st>>>(a);
+}
+void l_extract_flat(const ExtractArgs& a, cudaStream_t st) {
+    extract_kernel<KW, EX_FLAT><<<grid_for(a.n_lines, EX_WARPS, 148 * 8), EX_THREADS, 0, st>>>(a);
+}
+void l_partition_flat(const u64* flat_keys, const unsigned short* flat_meta, u64 n, u32 n_buckets, u64* bucket_cursor,
+                      u64* out_keys, unsigned short* out_meta, cudaStream_t st) {
+    if (n == 0) return;
+    partition_flat_kernel<KW><<<(unsigned)((n + PT_THREADS * PT_ITEMS - 1) / (PT_THREADS * PT_ITEMS)), PT_THREADS, 0, st>>>(
+        flat_keys, flat_meta, n, n_buckets, bucket_cursor, out_keys, out_meta);
 }
 void l_insert_records(const u64* keys, const unsigned short* meta, const u32* counts, u64 n, u64* table, u64 capacity,
                       Counters* ctr, cudaStream_t st) {
@@ -62,6 +71,8 @@ const EngineOps OPS = {KW,
                        l_init_table,
                        l_extract_insert,
                        l_extract_route,
+                       l_extract_flat,
+                       l_partition_flat,
                        l_insert_records,
                        l_rehash,
                        l_heads_count,

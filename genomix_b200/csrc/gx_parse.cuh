@@ -110,7 +110,7 @@ static __global__ void __launch_bounds__(PL_THREADS) parse_lines_kernel(const ui
     u64 bases = 0, occ = 0;
     LineDesc d;
     d.off[0] = d.off[1] = 0; d.len[0] = d.len[1] = 0; d.read_id = 0; d.flags = 0; d.pad = 0;
-    d.store[0] = d.store[1] = 0; d.head_idx[0] = d.head_idx[1] = 0;
+    d.store[0] = d.store[1] = 0; d.head_idx[0] = d.head_idx[1] = 0; d.occ_base = 0;
     if (i < n_lines) {
         const u32 start = (i == 0) ? 0u : nl_pos[i - 1] + 1u;
         u32 end = nl_pos[i];
@@ -182,7 +182,9 @@ static __global__ void __launch_bounds__(PL_THREADS) parse_lines_kernel(const ui
     u64 tot;
     const u64 packed = ((u64)store_bytes << 20) | (u64)n_split;
     const u64 ex = block_scan_excl<PL_THREADS>(packed, &tot);
-    __shared__ u64 base_heads, base_store;
+    __shared__ u64 base_heads, base_store, base_occ;
+    u64 occ_tot;
+    const u64 occ_ex = block_scan_excl<PL_THREADS>(occ, &occ_tot);
     if (threadIdx.x == 0) {
         base_heads = atomicAdd(&ctr->head_cursor, tot & 0xfffffull);
         base_store = atomicAdd(&ctr->store_cursor, tot >> 20);
@@ -199,7 +201,7 @@ static __global__ void __launch_bounds__(PL_THREADS) parse_lines_kernel(const ui
     if (threadIdx.x == 0) {
         atomicAdd(&ctr->chunk_reads, tot & 0xfffffull);
         atomicAdd(&ctr->chunk_store, tot >> 20);
-        atomicAdd(&ctr->chunk_occ, o_sum);
+        base_occ = atomicAdd(&ctr->chunk_occ, o_sum);
         atomicAdd(&ctr->reads, tot & 0xfffffull);
         atomicAdd(&ctr->bases, b_sum);
         atomicAdd(&ctr->occurrences, o_sum);
@@ -212,6 +214,7 @@ static __global__ void __launch_bounds__(PL_THREADS) parse_lines_kernel(const ui
         if (d.flags & 2u) d.head_idx[1] = h++;
         d.store[0] = s;
         d.store[1] = s + (d.len[0] + 3) / 4;
+        d.occ_base = base_occ + occ_ex;
         desc[i] = d;
     }
 }

@@ -27,7 +27,8 @@ class GenomixError(RuntimeError):
 
 class GraphBuilder:
     def __init__(self, kmer_length: int, device: int = 0, rank: int = 0, n_ranks: int = 1,
-                 expected_kmers: int = 0, chunk_bytes: int = 0, l2_fetch_granularity: int = 0):
+                 expected_kmers: int = 0, chunk_bytes: int = 0, l2_fetch_granularity: int = 0,
+                 blocked_mode: int = 0, blocked_buckets: int = 0):
         self._lib = _lib.load()
         cfg = GxConfig()
         cfg.abi_version = _lib.GX_ABI_VERSION
@@ -38,6 +39,8 @@ class GraphBuilder:
         cfg.expected_kmers = expected_kmers
         cfg.reserved[0] = chunk_bytes
         cfg.reserved[1] = l2_fetch_granularity or int(os.environ.get("GENOMIX_GB_L2_GRAN", "0"))
+        cfg.reserved[2] = blocked_mode or int(os.environ.get("GENOMIX_GB_BLOCKED", "0"))   # 0 auto, 1 never, 2 always
+        cfg.reserved[3] = blocked_buckets
         self.kmer_length = kmer_length
         self._ctx = C.c_void_p()
         st = self._lib.gx_create(C.byref(cfg), C.byref(self._ctx))

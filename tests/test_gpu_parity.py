@@ -65,6 +65,24 @@ def test_random_reads_match_oracle(k):
     assert got == oracle_canonical(k, text)
 
 
+@pytest.mark.parametrize("k,buckets", [(3, 2), (21, 7), (31, 64), (55, 5), (64, 1000), (91, 13), (128, 3)])
+def test_l2_blocked_build_matches_oracle(k, buckets):
+    """the L2-blocked path (flat extract -> partition by table region -> region-by-region insert), forced on a small
+    input, with growth in the middle of the region loop"""
+    gx = _gx()
+    rng = np.random.default_rng(2000 + k)
+    text = random_reads_text(rng, 300, k + 1, k + 60, paired=(k % 2 == 1), genome_len=max(3000, 30 * k))
+    want = oracle_canonical(k, text)
+    got, _ = gpu_canonical(k, text, blocked_mode=2, blocked_buckets=buckets)
+    assert got == want
+    got, _ = gpu_canonical(k, text, blocked_mode=2, blocked_buckets=buckets, chunk_bytes=3000)
+    assert got == want
+    with gx.GraphBuilder(k, blocked_mode=2, blocked_buckets=buckets, chunk_bytes=20000) as gb:
+        gb.push_lines(text)
+        gb.finish()
+        assert gx.types.canonical_records(gb.records()) == want
+
+
 def test_low_complexity_and_palindromes_even_k():
     """even k: palindromic k-mers tie to FORWARD; tandem repeats give self loops and multi-edges"""
     for k in (2, 4, 6, 32, 64):
