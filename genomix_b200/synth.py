@@ -43,6 +43,12 @@ CONFIGS = {
 }
 
 
+# single-GPU sized twins of the multi-GPU configs (same coverage / read length / error / k, smaller genome)
+CONFIGS["cfg3s"] = Workload("cfg3s", 6_250_000, 150, 60, 0.0, 55, paired=True, seed=3)
+CONFIGS["cfg4s"] = Workload("cfg4s", 6_687_500, 150, 100, 0.0, 55, seed=4)
+CONFIGS["cfg5s"] = Workload("cfg5s", 7_812_500, 250, 20, 0.02, 91, seed=5)
+
+
 def scaled(w: Workload, factor: float, name: str | None = None) -> Workload:
     return Workload(name or f"{w.name}/{factor:g}", max(int(w.genome_bp / factor), w.read_len * 4), w.read_len, w.coverage,
                     w.error, w.k, w.paired, w.seed, w.outer_mean, w.outer_std)
