@@ -14,7 +14,7 @@ EXPORTS = [
     "gx_abi_version", "gx_create", "gx_destroy", "gx_reset", "gx_last_error", "gx_get_stats",
     "gx_push_lines", "gx_push_lines_device", "gx_push_fastq", "gx_finish",
     "gx_num_nodes", "gx_record_bytes", "gx_next_records", "gx_records_device", "gx_next_frame",
-    "gx_partition_records", "gx_mg_unique_id", "gx_mg_init", "gx_mg_exchange",
+    "gx_partition_records", "gx_write_sequence_file", "gx_mg_unique_id", "gx_mg_init", "gx_mg_exchange",
     "gx_phase_ms", "gx_kernel_launches", "gx_set_stream",
 ]
 
@@ -77,6 +77,7 @@ def load() -> C.CDLL:
         "gx_records_device": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
         "gx_next_frame": (C.c_int, [vp, C.POINTER(u64), u8p, i32, C.POINTER(i32)]),
         "gx_partition_records": (C.c_int, [vp, i32, vp]),
+        "gx_write_sequence_file": (C.c_int, [vp, C.c_char_p, u8p, i32, i32, C.POINTER(u64)]),
         "gx_mg_unique_id": (C.c_int, [u8p]),
         "gx_mg_init": (C.c_int, [vp, u8p]),
         "gx_mg_exchange": (C.c_int, [vp]),

@@ -74,7 +74,7 @@ struct gx_ctx {
     u64 grows = 0;
 
     DevBuf heads, store;
-    DevBuf text, nl_pos, desc, tile_sums;
+    DevBuf text, nl_pos, nl_pos2, desc, tile_sums;
     DevBuf hslot, hcount, hstart, hperm, tile_bytes, tile_nodes, records, rec_offsets, parts, dense;
     DevBuf flat_keys, flat_meta, part_keys, part_meta, bucket_count;  // L2-blocked build
     int blocked_mode = 0;      // 0 auto, 1 never, 2 always (cfg.reserved[2]; tests and A/B runs)
@@ -359,36 +359,9 @@ int blocked_chunk(gx_ctx* c, const uint8_t* d_text, size_t n, u64 n_lines, u64 c
     return blocked_insert(c, (const u64*)c->part_keys.p, (const unsigned short*)c->part_meta.p, offsets, distinct);
 }
 
-// One chunk of text resident in device memory: line index -> parse -> reserve -> extract+insert.
-int push_chunk_device(gx_ctx* c, const uint8_t* d_text, size_t n) {
-    if (n == 0) return GX_OK;
-    if (n >= (1ull << 32) - 64) return fail(c, GX_ERR_INVALID, "chunk of %zu bytes exceeds the 4 GiB chunk limit", n);
-    const u64 n_tiles = (n + LI_TILE - 1) / LI_TILE;
-    u64 total_nl = 0;
-    {
-        ScopedPhase ph(c, PH_PARSE);
-        GX_TRY(ensure(c, c->tile_sums, (n_tiles + 1) * sizeof(u64)));
-        count_newlines_kernel<<<(unsigned)n_tiles, LI_THREADS, 0, c->stream>>>(d_text, n, (u64*)c->tile_sums.p);
-        GX_TRY(check_launch(c, "count_newlines"));
-        scan_tile_sums_kernel<<<1, 1024, 0, c->stream>>>((u64*)c->tile_sums.p, n_tiles, &c->d_ctr->scratch[0]);
-        GX_TRY(check_launch(c, "scan_tile_sums"));
-    }
-    GX_TRY(sync_counters(c));
-    total_nl = c->h_ctr->scratch[0];
-    const u64 max_lines = total_nl + 1;
-    {
-        ScopedPhase ph(c, PH_PARSE);
-        GX_TRY(ensure(c, c->nl_pos, (max_lines + 1) * sizeof(u32)));
-        GX_TRY(ensure(c, c->desc, max_lines * sizeof(LineDesc)));
-        write_newlines_kernel<<<(unsigned)n_tiles, LI_THREADS, 0, c->stream>>>(d_text, n, (const u64*)c->tile_sums.p,
-                                                                                (u32*)c->nl_pos.p);
-        GX_TRY(check_launch(c, "write_newlines"));
-        finish_line_index_kernel<<<1, 1, 0, c->stream>>>(d_text, n, &c->d_ctr->scratch[0], (u32*)c->nl_pos.p, c->d_ctr);
-        GX_TRY(check_launch(c, "finish_line_index"));
-        parse_lines_kernel<<<(unsigned)((max_lines + PL_THREADS - 1) / PL_THREADS), PL_THREADS, 0, c->stream>>>(
-            d_text, (const u32*)c->nl_pos.p, c->global_lines, c->k, (LineDesc*)c->desc.p, c->d_ctr);
-        GX_TRY(check_launch(c, "parse_lines"));
-    }
+// After a parse kernel filled c->desc for `n_lines` lines of the text at d_text: check errors, make room for heads,
+// packed reads and k-mers, then extract + insert.
+int insert_parsed_chunk(gx_ctx* c, const uint8_t* d_text, size_t n) {
     GX_TRY(sync_counters(c));
     const Counters& h = *c->h_ctr;
     const u64 n_lines = h.chunk_lines;
@@ -447,6 +420,77 @@ int push_chunk_device(gx_ctx* c, const uint8_t* d_text, size_t n) {
         }
     }
     return GX_OK;
+}
+
+
+// Line index of text[0, n): fills *nl_buf with the offsets of the line terminators (virtual one for an unterminated
+// last line) and returns an upper bound of the line count; the exact count is left in Counters::chunk_lines.
+int index_lines(gx_ctx* c, const uint8_t* d_text, size_t n, DevBuf& nl_buf, u64* max_lines) {
+    const u64 n_tiles = (n + LI_TILE - 1) / LI_TILE;
+    {
+        ScopedPhase ph(c, PH_PARSE);
+        GX_TRY(ensure(c, c->tile_sums, (n_tiles + 1) * sizeof(u64)));
+        count_newlines_kernel<<<(unsigned)n_tiles, LI_THREADS, 0, c->stream>>>(d_text, n, (u64*)c->tile_sums.p);
+        GX_TRY(check_launch(c, "count_newlines"));
+        scan_tile_sums_kernel<<<1, 1024, 0, c->stream>>>((u64*)c->tile_sums.p, n_tiles, &c->d_ctr->scratch[0]);
+        GX_TRY(check_launch(c, "scan_tile_sums"));
+    }
+    GX_TRY(sync_counters(c));
+    *max_lines = c->h_ctr->scratch[0] + 1;
+    {
+        ScopedPhase ph(c, PH_PARSE);
+        GX_TRY(ensure(c, nl_buf, (*max_lines + 1) * sizeof(u32)));
+        write_newlines_kernel<<<(unsigned)n_tiles, LI_THREADS, 0, c->stream>>>(d_text, n, (const u64*)c->tile_sums.p, (u32*)nl_buf.p);
+        GX_TRY(check_launch(c, "write_newlines"));
+        finish_line_index_kernel<<<1, 1, 0, c->stream>>>(d_text, n, &c->d_ctr->scratch[0], (u32*)nl_buf.p, c->d_ctr);
+        GX_TRY(check_launch(c, "finish_line_index"));
+    }
+    return GX_OK;
+}
+
+// One chunk of text resident in device memory: line index -> parse -> reserve -> extract+insert.
+int push_chunk_device(gx_ctx* c, const uint8_t* d_text, size_t n) {
+    if (n == 0) return GX_OK;
+    if (n >= (1ull << 32) - 64) return fail(c, GX_ERR_INVALID, "chunk of %zu bytes exceeds the 4 GiB chunk limit", n);
+    u64 max_lines = 0;
+    GX_TRY(index_lines(c, d_text, n, c->nl_pos, &max_lines));
+    {
+        ScopedPhase ph(c, PH_PARSE);
+        GX_TRY(ensure(c, c->desc, max_lines * sizeof(LineDesc)));
+        parse_lines_kernel<<<(unsigned)((max_lines + PL_THREADS - 1) / PL_THREADS), PL_THREADS, 0, c->stream>>>(
+            d_text, (const u32*)c->nl_pos.p, c->global_lines, c->k, (LineDesc*)c->desc.p, c->d_ctr);
+        GX_TRY(check_launch(c, "parse_lines"));
+    }
+    return insert_parsed_chunk(c, d_text, n);
+}
+
+// One chunk of fastq (r1 at [0, n1), r2 at [base2, base2 + n2) of the device text buffer; n2 == 0: single-end).
+int push_fastq_chunk_device(gx_ctx* c, const uint8_t* d_text, size_t n_total, size_t n1, size_t base2, size_t n2, u64 first_record) {
+    u64 max1 = 0, max2 = 0, lines1 = 0, lines2 = 0;
+    GX_TRY(index_lines(c, d_text, n1, c->nl_pos, &max1));
+    GX_TRY(sync_counters(c));
+    lines1 = c->h_ctr->chunk_lines;
+    if (n2) {
+        GX_TRY(index_lines(c, d_text + base2, n2, c->nl_pos2, &max2));
+        GX_TRY(sync_counters(c));
+        lines2 = c->h_ctr->chunk_lines;
+        if (lines1 != lines2)  // GenomixDriver.java:684-687
+            return c->sticky = fail(c, GX_ERR_FORMAT, "IOException: Fastq files didn't have the same number of lines! (%llu vs %llu)",
+                                    (unsigned long long)lines1, (unsigned long long)lines2);
+    }
+    const u64 n_records = (lines1 + 2) / 4;
+    if (n_records == 0) return GX_OK;
+    {
+        ScopedPhase ph(c, PH_PARSE);
+        GX_TRY(ensure(c, c->desc, n_records * sizeof(LineDesc)));
+        set_chunk_lines_kernel<<<1, 1, 0, c->stream>>>(c->d_ctr, n_records);
+        GX_TRY(check_launch(c, "set_chunk_lines"));
+        parse_fastq_kernel<<<(unsigned)((n_records + PL_THREADS - 1) / PL_THREADS), PL_THREADS, 0, c->stream>>>(
+            d_text, (const u32*)c->nl_pos.p, lines1, (u32)base2, (const u32*)c->nl_pos2.p, n2 ? 1 : 0, first_record,
+            c->global_lines, c->k, (LineDesc*)c->desc.p, c->d_ctr);
+        GX_TRY(check_launch(c, "parse_fastq"));
+    }
+    return insert_parsed_chunk(c, d_text, n_total);
 }
 
 int require_live(gx_ctx* c) {
@@ -553,7 +597,7 @@ void gx_destroy(gx_ctx* c) {
     drain_timers(c);
     mg_destroy(c);
     for (auto e : c->event_pool) cudaEventDestroy(e);
-    DevBuf* bufs[] = {&c->heads, &c->store, &c->text, &c->nl_pos, &c->desc, &c->tile_sums, &c->hslot, &c->hcount, &c->hstart,
+    DevBuf* bufs[] = {&c->heads, &c->store, &c->text, &c->nl_pos, &c->nl_pos2, &c->desc, &c->tile_sums, &c->hslot, &c->hcount, &c->hstart,
                       &c->hperm, &c->tile_bytes, &c->tile_nodes, &c->records, &c->rec_offsets, &c->parts, &c->dense,
                       &c->flat_keys, &c->flat_meta, &c->part_keys, &c->part_meta, &c->bucket_count};
     for (auto* b : bufs) release(*b);
@@ -639,9 +683,25 @@ int gx_push_lines(gx_ctx* c, const uint8_t* host_text, size_t n_bytes) {
     return GX_OK;
 }
 
-int gx_push_fastq(gx_ctx* c, const uint8_t*, size_t, const uint8_t*, size_t, uint64_t) {
+int gx_push_fastq(gx_ctx* c, const uint8_t* host_r1, size_t n1, const uint8_t* host_r2, size_t n2, uint64_t first_record) {
     GX_TRY(require_live(c));
-    return fail(c, GX_ERR_STATE, "gx_push_fastq: not implemented in this build");
+    if (c->finished) return fail(c, GX_ERR_STATE, "gx_push_fastq after gx_finish (call gx_reset first)");
+    if ((!host_r1 && n1) || (!host_r2 && n2)) return fail(c, GX_ERR_INVALID, "null fastq buffer");
+    if (n1 + n2 + 64 >= (1ull << 32)) return fail(c, GX_ERR_INVALID, "fastq chunk pair exceeds the 4 GiB chunk limit; push smaller chunks");
+    if (n1 == 0 && n2 == 0) return GX_OK;
+    cudaSetDevice(c->cfg.device);
+    const size_t base2 = (n1 + 15) & ~(size_t)15;
+    const size_t total = host_r2 ? base2 + n2 : n1;
+    GX_TRY(ensure(c, c->text, total));
+    {
+        ScopedPhase ph(c, PH_H2D);
+        CUDA_TRY(c, cudaMemcpyAsync(c->text.p, host_r1, n1, cudaMemcpyHostToDevice, c->stream));
+        if (host_r2 && n2) CUDA_TRY(c, cudaMemcpyAsync((uint8_t*)c->text.p + base2, host_r2, n2, cudaMemcpyHostToDevice, c->stream));
+    }
+    GX_TRY(push_fastq_chunk_device(c, (const uint8_t*)c->text.p, total, n1, base2, host_r2 ? n2 : 0, first_record));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    drain_timers(c);
+    return GX_OK;
 }
 
 int gx_finish(gx_ctx* c) {
@@ -848,6 +908,78 @@ int gx_partition_records(gx_ctx* c, int32_t n_parts, int32_t* host_parts) {
     GX_TRY(check_launch(c, "partition_records"));
     CUDA_TRY(c, cudaMemcpyAsync(host_parts, c->parts.p, c->n_nodes * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return GX_OK;
+}
+
+// R4: SequenceFile v6 writer (hadoop-core 0.20.2 SequenceFile.Writer restated: header, append(), checkAndWriteSync()).
+int gx_write_sequence_file(gx_ctx* c, const char* path, const uint8_t* sync16, int32_t n_parts, int32_t part,
+                           uint64_t* bytes_written) {
+    GX_TRY(require_live(c));
+    if (!c->finished) return fail(c, GX_ERR_STATE, "gx_write_sequence_file before gx_finish");
+    if (!path || n_parts < 0 || (n_parts > 0 && (part < 0 || part >= n_parts))) return fail(c, GX_ERR_INVALID, "bad argument");
+    cudaSetDevice(c->cfg.device);
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(c, GX_ERR_INVALID, "cannot open %s for writing", path);
+    uint8_t sync[16];
+    if (sync16) memcpy(sync, sync16, 16);
+    else {  // hadoop uses an MD5 of a fresh UID + time; any 16 bytes are valid -- derive them from the path
+        u64 h0 = 0x9e3779b97f4a7c15ull, h1 = 0xd6e8feb86659fd93ull;
+        for (const char* q = path; *q; ++q) { h0 = mix64(h0 ^ (u64)(unsigned char)*q); h1 = mix64(h1 + h0); }
+        memcpy(sync, &h0, 8); memcpy(sync + 8, &h1, 8);
+    }
+    u64 pos = 0, last_sync = 0;
+    bool io_ok = true;
+    auto put = [&](const void* p, size_t nbytes) { if (nbytes && fwrite(p, 1, nbytes, f) != nbytes) io_ok = false; pos += nbytes; };
+    auto put_string = [&](const char* str) {  // Text.writeString: vint length (one byte below 128) + UTF-8
+        const uint8_t len = (uint8_t)strlen(str);
+        put(&len, 1);
+        put(str, len);
+    };
+    const uint8_t magic[4] = {'S', 'E', 'Q', 6};
+    put(magic, 4);
+    put_string("edu.uci.ics.genomix.data.types.VKmer");
+    put_string("edu.uci.ics.genomix.data.types.Node");
+    const uint8_t flags[2] = {0, 0};  // compressed, blockCompressed
+    put(flags, 2);
+    const uint8_t zero4[4] = {0, 0, 0, 0};
+    put(zero4, 4);                    // metadata: 0 entries
+    put(sync, 16);
+    const uint8_t escape[4] = {0xff, 0xff, 0xff, 0xff};
+    auto be32 = [](const uint8_t* p) { return ((u32)p[0] << 24) | ((u32)p[1] << 16) | ((u32)p[2] << 8) | (u32)p[3]; };
+    // stream the records through a pinned slab
+    const size_t SLAB = 64ull << 20;
+    uint8_t* slab = nullptr;
+    CUDA_TRY(c, cudaMallocHost((void**)&slab, SLAB));
+    int rc = GX_OK;
+    u64 cursor = 0;
+    while (cursor < c->record_bytes && io_ok) {
+        size_t used = 0;
+        uint64_t cur = cursor;
+        rc = gx_next_records(c, &cur, slab, SLAB, &used);
+        if (rc != GX_OK || used == 0) break;
+        for (size_t off = 0; off < used;) {
+            const u32 rec_len = be32(slab + off);
+            const u32 key_len = be32(slab + off + 4);
+            bool mine = true;
+            if (n_parts > 0) {  // KmerPartitionComputerFactory.partition on the Kmer bytes (VKmer minus its 4-byte header)
+                int h = 1;
+                for (u32 j = 4; j < key_len; ++j) h = 31 * h + (int)(signed char)slab[off + 8 + j];
+                if (h < 0) h = -(h + 1);
+                mine = (h % n_parts) == part;
+            }
+            if (mine) {
+                if (pos >= last_sync + 2000) { put(escape, 4); put(sync, 16); last_sync = pos; }  // checkAndWriteSync
+                put(slab + off, 8 + (size_t)rec_len);
+            }
+            off += 8 + (size_t)rec_len;
+        }
+        cursor = cur;
+    }
+    cudaFreeHost(slab);
+    if (fclose(f) != 0) io_ok = false;
+    if (rc != GX_OK) return rc;
+    if (!io_ok) return fail(c, GX_ERR_INVALID, "I/O error while writing %s", path);
+    if (bytes_written) *bytes_written = pos;
     return GX_OK;
 }
 

@@ -92,11 +92,87 @@ static __global__ void finish_line_index_kernel(const uint8_t* __restrict__ text
     ctr->chunk_max_line_occ = 0;
 }
 
+static __global__ void set_chunk_lines_kernel(Counters* ctr, u64 n) {
+    ctr->chunk_lines = n;
+    ctr->chunk_reads = 0;
+    ctr->chunk_occ = 0;
+    ctr->chunk_store = 0;
+    ctr->chunk_max_line_occ = 0;
+}
+
 __device__ __forceinline__ void report_line_error(Counters* ctr, u64 global_line, u32 code) {
     atomicMin(&ctr->error, (global_line << 8) | (u64)code);
 }
 
 static constexpr int PL_THREADS = 256;
+
+// Per-mate checks in the order the reference hits them (ReadsKeyValueParserFactory.java:125-145): regex, then
+// makeUUID's readId guard (ReadHeadInfo.java:110-113), then k >= length (:152-155). Fills the split flags and
+// this line's contribution to the counters.
+__device__ __forceinline__ void validate_mates(LineDesc& d, bool has_mate_field, bool neg, u64 mag, bool ok0, bool ok1, int k,
+                                               u64 gline, Counters* ctr, u32& n_split, u32& store_bytes, u64& bases, u64& occ) {
+    const bool v0 = ok0 && d.len[0] > 0;
+    const bool v1 = has_mate_field && ok1 && d.len[1] > 0;
+    const bool id_bad = neg || mag >= (1ull << 29);
+    bool dead = false;
+    if (v0) {
+        if (id_bad) { report_line_error(ctr, gline, LE_READID); dead = true; }
+        else if ((u32)k >= d.len[0]) { report_line_error(ctr, gline, LE_TOO_SHORT); dead = true; }
+    }
+    if (!dead && v1) {
+        if (id_bad) { report_line_error(ctr, gline, LE_READID); dead = true; }
+        else if ((u32)k >= d.len[1]) { report_line_error(ctr, gline, LE_TOO_SHORT); dead = true; }
+    }
+    if (!dead) {
+        if (v0) { d.flags |= 1u; ++n_split; bases += d.len[0]; occ += d.len[0] - k + 1; }
+        if (v1) { d.flags |= 2u; ++n_split; bases += d.len[1]; occ += d.len[1] - k + 1; }
+        if (n_split) store_bytes = (d.len[0] + 3) / 4 + (d.len[1] + 3) / 4;
+    }
+}
+
+// Reserve head indices, read-store bytes and flat occurrence indices for the CTA's lines (one atomic each per CTA),
+// update the job counters, and store the descriptor.
+template <int NT>
+__device__ __forceinline__ void reserve_and_store(LineDesc& d, bool in_range, u64 i, u32 n_split, u32 store_bytes, u64 bases,
+                                                  u64 occ, LineDesc* __restrict__ desc, Counters* __restrict__ ctr) {
+    u64 tot;
+    const u64 packed = ((u64)store_bytes << 20) | (u64)n_split;
+    const u64 ex = block_scan_excl<NT>(packed, &tot);
+    __shared__ u64 base_heads, base_store, base_occ;
+    u64 occ_tot;
+    const u64 occ_ex = block_scan_excl<NT>(occ, &occ_tot);
+    if (threadIdx.x == 0) {
+        base_heads = atomicAdd(&ctr->head_cursor, tot & 0xfffffull);
+        base_store = atomicAdd(&ctr->store_cursor, tot >> 20);
+    }
+    const u64 b_sum = block_reduce_sum<NT>(bases);
+    const u64 o_sum = block_reduce_sum<NT>(occ);
+    {   // per-line maximum: warp reduce, one atomic per warp that has something to report
+        u64 mx = occ;
+#pragma unroll
+        for (int dl = 16; dl > 0; dl >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, dl));
+        if ((threadIdx.x & 31) == 0 && mx > 0 && mx > ctr->chunk_max_line_occ) atomicMax(&ctr->chunk_max_line_occ, mx);
+    }
+    if (threadIdx.x == 0) {
+        atomicAdd(&ctr->chunk_reads, tot & 0xfffffull);
+        atomicAdd(&ctr->chunk_store, tot >> 20);
+        base_occ = atomicAdd(&ctr->chunk_occ, o_sum);
+        atomicAdd(&ctr->reads, tot & 0xfffffull);
+        atomicAdd(&ctr->bases, b_sum);
+        atomicAdd(&ctr->occurrences, o_sum);
+    }
+    __syncthreads();
+    if (in_range) {
+        u64 h = base_heads + (ex & 0xfffffull);
+        const u64 s = base_store + (ex >> 20);
+        if (d.flags & 1u) d.head_idx[0] = h++;
+        if (d.flags & 2u) d.head_idx[1] = h++;
+        d.store[0] = s;
+        d.store[1] = s + (d.len[0] + 3) / 4;
+        d.occ_base = base_occ + occ_ex;
+        desc[i] = d;
+    }
+}
 
 // One thread per line.
 static __global__ void __launch_bounds__(PL_THREADS) parse_lines_kernel(const uint8_t* __restrict__ text,
@@ -159,64 +235,56 @@ static __global__ void __launch_bounds__(PL_THREADS) parse_lines_kernel(const ui
             d.read_id = neg ? (u64)(-(long long)mag) : mag;
             d.off[0] = fs[1]; d.len[0] = fe[1] - fs[1];
             if (nf == 3) { d.off[1] = fs[2]; d.len[1] = fe[2] - fs[2]; d.flags |= 4u; }
-            const bool v0 = ok0 && d.len[0] > 0;
-            const bool v1 = (nf == 3) && ok1 && d.len[1] > 0;
-            // guards in the order the reference hits them: makeUUID (ReadHeadInfo.java:110-113) then k >= len (:152-155)
-            const bool id_bad = neg || mag >= (1ull << 29);
-            if (v0) {
-                if (id_bad) { report_line_error(ctr, gline, LE_READID); dead = true; }
-                else if ((u32)k >= d.len[0]) { report_line_error(ctr, gline, LE_TOO_SHORT); dead = true; }
-            }
-            if (!dead && v1) {
-                if (id_bad) { report_line_error(ctr, gline, LE_READID); dead = true; }
-                else if ((u32)k >= d.len[1]) { report_line_error(ctr, gline, LE_TOO_SHORT); dead = true; }
-            }
-            if (!dead) {
-                if (v0) { d.flags |= 1u; ++n_split; bases += d.len[0]; occ += d.len[0] - k + 1; }
-                if (v1) { d.flags |= 2u; ++n_split; bases += d.len[1]; occ += d.len[1] - k + 1; }
-                if (n_split) store_bytes = (d.len[0] + 3) / 4 + (d.len[1] + 3) / 4;
-            }
+            validate_mates(d, nf == 3, neg, mag, ok0, ok1, k, gline, ctr, n_split, store_bytes, bases, occ);
         }
     }
-    // ---- reserve head indices and read-store bytes: one atomic pair per CTA
-    u64 tot;
-    const u64 packed = ((u64)store_bytes << 20) | (u64)n_split;
-    const u64 ex = block_scan_excl<PL_THREADS>(packed, &tot);
-    __shared__ u64 base_heads, base_store, base_occ;
-    u64 occ_tot;
-    const u64 occ_ex = block_scan_excl<PL_THREADS>(occ, &occ_tot);
-    if (threadIdx.x == 0) {
-        base_heads = atomicAdd(&ctr->head_cursor, tot & 0xfffffull);
-        base_store = atomicAdd(&ctr->store_cursor, tot >> 20);
-    }
-    const u64 b_sum = block_reduce_sum<PL_THREADS>(bases);
-    const u64 o_sum = block_reduce_sum<PL_THREADS>(occ);
-    // per-line maximum: warp reduce, one atomic per warp that has something to report
-    {
-        u64 mx = occ;
+    reserve_and_store<PL_THREADS>(d, i < n_lines, i, n_split, store_bytes, bases, occ, desc, ctr);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// R6 fused with R1: fastq records -> the same LineDesc the text parser produces.
+// GenomixDriver.convertAndUploadFastqToHDFS (GenomixDriver.java:665-714): record i of the file is 0-based line 4i+1,
+// its id is the post-incremented line number 4i+2, the sequence (and the mate's, read in lock step from the second
+// file) is String.trim()med. The text line it would have written is then parsed by ReadsKeyValueParserFactory.parse,
+// so an empty (trimmed) sequence leaves the line with too few fields -> the same IllegalStateException.
+static __global__ void __launch_bounds__(PL_THREADS) parse_fastq_kernel(const uint8_t* __restrict__ text,
+                                                                 const u32* __restrict__ nl1, u64 n_lines1,
+                                                                 u32 base2, const u32* __restrict__ nl2, int paired,
+                                                                 u64 first_record, u64 first_global_line, int k,
+                                                                 LineDesc* __restrict__ desc, Counters* __restrict__ ctr) {
+    const u64 i = (u64)blockIdx.x * PL_THREADS + threadIdx.x;
+    const u64 n_records = (n_lines1 + 2) / 4;  // records whose sequence line 4i+1 exists
+    u32 n_split = 0, store_bytes = 0;
+    u64 bases = 0, occ = 0;
+    LineDesc d;
+    d.off[0] = d.off[1] = 0; d.len[0] = d.len[1] = 0; d.read_id = 0; d.flags = 0; d.pad = 0;
+    d.store[0] = d.store[1] = 0; d.head_idx[0] = d.head_idx[1] = 0; d.occ_base = 0;
+    if (i < n_records) {
+        const u64 j = 4 * i + 1;
+        bool ok[2] = {true, true};
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-        if ((threadIdx.x & 31) == 0 && mx > 0 && mx > ctr->chunk_max_line_occ) atomicMax(&ctr->chunk_max_line_occ, mx);
+        for (int m = 0; m < 2; ++m) {
+            if (m == 1 && !paired) break;
+            const u32* nl = m ? nl2 : nl1;
+            const u32 b = m ? base2 : 0u;
+            u32 s = b + nl[j - 1] + 1u, e = b + nl[j];
+            while (s < e && __ldg(text + s) <= ' ') ++s;          // String.trim(): strips chars <= U+0020 at both ends
+            while (e > s && __ldg(text + e - 1) <= ' ') --e;
+            d.off[m] = s; d.len[m] = e - s;
+            for (u32 p = s; p < e; ++p) { bool c_ok; (void)code_of(__ldg(text + p), c_ok); ok[m] = ok[m] && c_ok; }
+        }
+        const u64 id = 4 * (first_record + i) + 2;
+        d.read_id = id;
+        const u64 gline = first_global_line + i;
+        // fields of the text line "<id>\t<seq>[\t<mate>]" after String.split drops trailing empty strings
+        const int nf = paired ? (d.len[1] ? 3 : (d.len[0] ? 2 : 1)) : (d.len[0] ? 2 : 1);
+        if (nf < 2) report_line_error(ctr, gline, LE_FORMAT);
+        else {
+            if (nf == 3) d.flags |= 4u; else { d.len[1] = 0; }
+            validate_mates(d, nf == 3, false, id, ok[0], ok[1], k, gline, ctr, n_split, store_bytes, bases, occ);
+        }
     }
-    if (threadIdx.x == 0) {
-        atomicAdd(&ctr->chunk_reads, tot & 0xfffffull);
-        atomicAdd(&ctr->chunk_store, tot >> 20);
-        base_occ = atomicAdd(&ctr->chunk_occ, o_sum);
-        atomicAdd(&ctr->reads, tot & 0xfffffull);
-        atomicAdd(&ctr->bases, b_sum);
-        atomicAdd(&ctr->occurrences, o_sum);
-    }
-    __syncthreads();
-    if (i < n_lines) {
-        u64 h = base_heads + (ex & 0xfffffull);
-        u64 s = base_store + (ex >> 20);
-        if (d.flags & 1u) d.head_idx[0] = h++;
-        if (d.flags & 2u) d.head_idx[1] = h++;
-        d.store[0] = s;
-        d.store[1] = s + (d.len[0] + 3) / 4;
-        d.occ_base = base_occ + occ_ex;
-        desc[i] = d;
-    }
+    reserve_and_store<PL_THREADS>(d, i < n_records, i, n_split, store_bytes, bases, occ, desc, ctr);
 }
 
 }  // namespace gx

@@ -87,6 +87,17 @@ class GraphBuilder:
     def push_lines_device(self, dev_ptr: int, n_bytes: int) -> None:
         self._check(self._lib.gx_push_lines_device(self._ctx, C.c_void_p(dev_ptr), n_bytes))
 
+    def push_fastq(self, r1, r2=None, first_record: int = 0) -> None:
+        """Whole-record-aligned chunk(s) of uncompressed fastq (host buffers); r2 is the mate file's chunk holding the same
+        records. Read ids are the reference's 4*i+2 with i counted from first_record (GenomixDriver.java:665-714)."""
+        p1, n1, k1 = _host_ptr(r1)
+        if r2 is None:
+            p2, n2, k2 = None, 0, None
+        else:
+            p2, n2, k2 = _host_ptr(r2)
+        self._check(self._lib.gx_push_fastq(self._ctx, p1, n1, p2, n2, first_record))
+        del k1, k2
+
     def finish(self) -> None:
         self._check(self._lib.gx_finish(self._ctx))
 
@@ -160,6 +171,17 @@ class GraphBuilder:
             if n_tuples.value == 0:
                 return
             yield frame.tobytes()
+
+    def write_sequence_file(self, path: str, sync: bytes | None = None, n_parts: int = 0, part: int = 0) -> int:
+        """Write `part-<part>` as an uncompressed SequenceFile v6 <VKmer,Node> (what KmerNodePairSequenceWriterFactory
+        produces); returns the bytes written. n_parts == 0 writes every record."""
+        written = C.c_uint64(0)
+        sp = None
+        if sync is not None:
+            assert len(sync) == 16
+            sp = C.cast(C.create_string_buffer(sync, 16), C.c_void_p)
+        self._check(self._lib.gx_write_sequence_file(self._ctx, path.encode(), sp, n_parts, part, C.byref(written)))
+        return int(written.value)
 
     def partition(self, n_parts: int) -> np.ndarray:
         """KmerPartitionComputerFactory.partition for every emitted record (Java hash, abs, % n_parts)."""

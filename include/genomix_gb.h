@@ -127,6 +127,16 @@ int gx_records_device(gx_ctx* ctx, const uint8_t** dev_records, const uint64_t**
  * frame is GX_ERR_BUFFER (ReadsKeyValueParserFactory.java:245-249). */
 int gx_next_frame(gx_ctx* ctx, uint64_t* cursor, uint8_t* host_frame, int32_t frame_size, int32_t* n_tuples);
 
+/* R4 complete: write the record stream as an uncompressed SequenceFile v6 <VKmer,Node> part file, byte-compatible with
+ * what SequenceFile.createWriter(conf, out, VKmer.class, Node.class, CompressionType.NONE, null) + append() produce
+ * (KmerNodePairSequenceWriterFactory.java:66-94; hadoop-core 0.20.2 SequenceFile.Writer): header "SEQ\6", the two
+ * class names, no compression, empty metadata, the 16-byte sync marker; then records, with a sync escape
+ * (int -1 + marker) before a record whenever >= 2000 bytes were written since the last sync. `sync16` is the
+ * marker (hadoop draws it at random; pass NULL for a marker derived from the file name). If n_parts > 0 only the
+ * records whose Java partition hash % n_parts == part are written (part-<part> of an n_parts job). */
+int gx_write_sequence_file(gx_ctx* ctx, const char* path, const uint8_t* sync16, int32_t n_parts, int32_t part,
+                           uint64_t* bytes_written);
+
 /* ---- R3: partitioner ---------------------------------------------------------------------------
  * Batched KmerPartitionComputerFactory.partition over the record stream (Java 31-polynomial hash,
  * abs, % n_parts): writes one int32 per node into host_parts (n_nodes entries). */

@@ -428,6 +428,44 @@ def graph_records(k: int, table: dict) -> dict:
     return {vkmer_bytes(k, key): node.write() for key, node in table.items()}
 
 
+# ----------------------------------------------------------------------------- A0 fastq conversion
+def java_trim(b: bytes) -> bytes:
+    """String.trim(): strips code points <= U+0020 from both ends."""
+    s, e = 0, len(b)
+    while s < e and b[s] <= 0x20:
+        s += 1
+    while e > s and b[e - 1] <= 0x20:
+        e -= 1
+    return b[s:e]
+
+
+def java_read_lines(data: bytes) -> list:
+    """BufferedReader.readLine(): lines end at \n, \r or \r\n; a final unterminated line counts."""
+    lines = re.split(rb"\r\n|\n|\r", data)
+    if lines and lines[-1] == b"":
+        lines.pop()
+    return lines
+
+
+def fastq_to_readids(mate1: bytes, mate2: bytes | None = None) -> bytes:
+    """genomix-driver/.../GenomixDriver.java:665-714 convertAndUploadFastqToHDFS: 0-based line j with j % 4 == 1 is
+    written as '<j+1>\t<line.trim()>[\t<mateLine.trim()>]\n'; paired files of different line counts are an IOException."""
+    l1 = java_read_lines(mate1)
+    out = []
+    if mate2 is not None:
+        l2 = java_read_lines(mate2)
+        if len(l1) != len(l2):
+            raise GraphBuildError("IOException: Fastq files didn't have the same number of lines")
+        for j, (a, b) in enumerate(zip(l1, l2)):
+            if j % 4 == 1:
+                out.append(b"%d\t%s\t%s\n" % (j + 1, java_trim(a), java_trim(b)))
+    else:
+        for j, a in enumerate(l1):
+            if j % 4 == 1:
+                out.append(b"%d\t%s\n" % (j + 1, java_trim(a)))
+    return b"".join(out)
+
+
 # ----------------------------------------------------------------------------- A8 partition hash
 def java_partition(key: bytes, n_parts: int) -> int:
     """GH/data/primitive/KmerPartitionComputerFactory.java:28-33,39-52."""
