@@ -634,3 +634,111 @@ int gxo_build(const uint8_t* text, size_t n, int k, int n_threads, uint8_t** out
 void gxo_free(uint8_t* p) { free(p); }
 
 int gxo_java_partition(const uint8_t* key, int n, int n_parts) { return java_partition(key, n, n_parts); }
+
+/* ------------------------------------------------------------------------------------------------ canonical checksum
+ * Order-independent fingerprint of a record stream (recordLength | keyLength | VKmer | Node ...): the sum over records
+ * of a 64-bit hash of (key, per-type SET of neighbour VKmers, unflipped/flipped read-head lists, coverage). Two streams
+ * have the same fingerprint iff (up to 2^-64 collisions) they hold the same records after canonical sorting -- the
+ * comparison rule of the reference's tests (utils/TestUtils.java:67-181: record order and VKmerList order are free). */
+static uint64_t fp_mix(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return x;
+}
+static uint64_t fp_bytes(const uint8_t* p, size_t n, uint64_t seed) {
+    uint64_t h = seed ^ (0x9e3779b97f4a7c15ull * (n + 1));
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) { uint64_t w; memcpy(&w, p + i, 8); h = fp_mix(h ^ w) + 0x9e3779b97f4a7c15ull; }
+    uint64_t w = 0;
+    if (i < n) memcpy(&w, p + i, n - i);
+    return fp_mix(h ^ w ^ ((uint64_t)(n - i) << 56));
+}
+
+typedef struct { uint64_t sum, xor_, records, heads, edges; double coverage_total; int32_t bad; } gxo_fingerprint;
+
+int gxo_canonical_fingerprint(const uint8_t* stream, size_t n, gxo_fingerprint* out) {
+    gxo_fingerprint f; memset(&f, 0, sizeof f);
+    size_t off = 0;
+    while (off + 8 <= n) {
+        uint32_t rec_len = get32(stream + off), key_len = get32(stream + off + 4);
+        if (off + 8 + rec_len > n || key_len > rec_len) { f.bad = 1; break; }
+        const uint8_t* key = stream + off + 8;
+        const uint8_t* p = key + key_len;
+        const uint8_t* end = stream + off + 8 + rec_len;
+        uint64_t h = fp_bytes(key, key_len, 1);
+        uint8_t active = *p++;
+        h = fp_mix(h ^ active);
+        for (int et = 0; et < 4; et++) {
+            if (!(active & (1 << et))) continue;
+            uint32_t cnt = get32(p); p += 4;
+            uint64_t set_sum = 0;
+            for (uint32_t i = 0; i < cnt; i++) {
+                int len = 4 + byte_num_from_k((int)get32(p));
+                set_sum += fp_bytes(p, (size_t)len, 100 + (uint64_t)et);   /* order-free inside the list */
+                p += len;
+            }
+            h = fp_mix(h ^ set_sum ^ ((uint64_t)cnt << 40));
+            f.edges += cnt;
+        }
+        for (int s = 0; s < 2; s++) {
+            if (!(active & (1 << (4 + s)))) continue;
+            const uint8_t* start = p;
+            p += 1;
+            uint32_t cnt = get32(p); p += 4;
+            for (uint32_t i = 0; i < cnt; i++) {
+                uint8_t flags = *p++;
+                p += 8;
+                p += 4 + byte_num_from_k((int)get32(p));
+                if (flags & 1) p += 4 + byte_num_from_k((int)get32(p));
+            }
+            h = fp_mix(h ^ fp_bytes(start, (size_t)(p - start), 200 + (uint64_t)s));  /* TreeSet order is part of the format */
+            f.heads += cnt;
+        }
+        if (active & (1 << 6)) { p += 4 + byte_num_from_k((int)get32(p)); }
+        if (active & (1 << 7)) {
+            uint32_t u = get32(p); float c; memcpy(&c, &u, 4);
+            f.coverage_total += c;
+            h = fp_mix(h ^ u);
+            p += 4;
+        }
+        if (p != end) { f.bad = 2; break; }
+        f.sum += h; f.xor_ ^= h; f.records++;
+        off += 8 + rec_len;
+    }
+    if (off != n && !f.bad) f.bad = 3;
+    *out = f;
+    return f.bad;
+}
+
+/* Edge symmetry: every adjacency is recorded on both nodes (setEdgesForCurAndNext, ReadsKeyValueParserFactory.java:209-233:
+ * cur.edges[t] += next, next.edges[mirror(t)] += cur), so the signed sum over all (node X, type t, neighbour Y) of
+ * E(X,t,Y) - E(Y,mirror(t),X) must vanish. Returns that sum (0 = symmetric, w.h.p.) and the edge count. */
+static uint64_t edge_hash(const uint8_t* x, const uint8_t* y, int vk_len, int t) {
+    return fp_mix(fp_bytes(x, (size_t)vk_len, 7) * 0x9e3779b97f4a7c15ull + fp_bytes(y, (size_t)vk_len, 11) + (uint64_t)t * 0xd6e8feb86659fd93ull);
+}
+int gxo_edge_symmetry(const uint8_t* stream, size_t n, uint64_t* signed_sum, uint64_t* n_edges) {
+    static const int mirror[4] = {3, 1, 2, 0}; /* EDGETYPE.mirror, types/EDGETYPE.java:44-58 */
+    uint64_t acc = 0, edges = 0;
+    size_t off = 0;
+    while (off + 8 <= n) {
+        uint32_t rec_len = get32(stream + off), key_len = get32(stream + off + 4);
+        if (off + 8 + rec_len > n) return 1;
+        const uint8_t* key = stream + off + 8;
+        const uint8_t* p = key + key_len;
+        uint8_t active = *p++;
+        for (int et = 0; et < 4; et++) {
+            if (!(active & (1 << et))) continue;
+            uint32_t cnt = get32(p); p += 4;
+            for (uint32_t i = 0; i < cnt; i++) {
+                int len = 4 + byte_num_from_k((int)get32(p));
+                if ((uint32_t)len != key_len) return 2; /* graph build only links k-mers of the same k */
+                acc += edge_hash(key, p, len, et);
+                acc -= edge_hash(p, key, len, mirror[et]);
+                edges++;
+                p += len;
+            }
+        }
+        off += 8 + rec_len;
+    }
+    *signed_sum = acc; *n_edges = edges;
+    return 0;
+}
