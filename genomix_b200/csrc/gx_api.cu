@@ -92,6 +92,14 @@ struct gx_ctx {
 
     void* mg = nullptr;  // MgState (gx_mg.inl) when n_ranks > 1
 
+    // spill area (two buffers, swapped while one is being re-inserted) and the new-key predictor
+    DevBuf spill_keys[2], spill_meta[2];
+    int spill_cur = 0;
+    u64 spill_cap = 0;
+    bool test_no_new_keys = false;
+    double new_key_ratio = -1.0;   // new keys per occurrence in the last measured interval (< 0: unknown)
+    u64 ratio_distinct0 = 0, ratio_pending_occ = 0;
+
     float phase_ms[PH_COUNT] = {0};
     std::vector<PendingTimer> timers;
     std::vector<cudaEvent_t> event_pool;
@@ -284,6 +292,68 @@ int reserve_room(gx_ctx* c, u64 distinct, u64 min_room, u64 hint, u64* room) {
     }
 }
 
+// ---- new-key predictor --------------------------------------------------------------------------------------
+// Every occurrence could be a new key, but in sequencing data most are repeats (coverage). After each counter sync
+// the host measures new keys per occurrence over the batches launched since the previous sync and sizes the next
+// batch for twice that rate plus a margin. If the prediction is too low the table runs past GROW_LOAD; should it
+// actually fill up, upserts spill (Counters::spill_*) and handle_spills() grows the table and re-inserts them.
+void note_sync(gx_ctx* c, u64 distinct_now) {
+    if (c->ratio_pending_occ) {
+        c->new_key_ratio = (double)(distinct_now - c->ratio_distinct0) / (double)c->ratio_pending_occ;
+        c->ratio_pending_occ = 0;
+    }
+    c->ratio_distinct0 = distinct_now;
+}
+u64 predict_new_keys(const gx_ctx* c, u64 occ) {
+    if (c->test_no_new_keys) return occ ? 1 : 0;
+    if (c->new_key_ratio < 0) return occ;
+    const double p = 2.0 * c->new_key_ratio * (double)occ + (double)occ / 64.0 + 65536.0;
+    return p >= (double)occ ? occ : (u64)p;
+}
+
+int set_spill_target(gx_ctx* c) {
+    struct { u64 count, cap; u64* keys; unsigned short* meta; } t = {0, c->spill_cap, (u64*)c->spill_keys[c->spill_cur].p,
+                                                                     (unsigned short*)c->spill_meta[c->spill_cur].p};
+    static_assert(offsetof(Counters, spill_meta) - offsetof(Counters, spill_count) == 24, "spill fields are contiguous");
+    CUDA_TRY(c, cudaMemcpyAsync(&c->d_ctr->spill_count, &t, sizeof t, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return GX_OK;
+}
+
+int grow_table(gx_ctx* c) {
+    const u64 ncap = c->capacity * 2;
+    u64* nt = nullptr;
+    GX_TRY(alloc_table(c, ncap, &nt));
+    c->ops->rehash(c->table, c->capacity, nt, ncap, c->stream);
+    GX_TRY(check_launch(c, "rehash"));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaFree(c->table));
+    ++c->grows;
+    c->table = nt;
+    c->capacity = ncap;
+    return GX_OK;
+}
+
+// Call after sync_counters(): re-insert records that spilled because the table was fuller than predicted.
+int handle_spills(gx_ctx* c) {
+    while (c->h_ctr->spill_count > 0) {
+        if (c->h_ctr->table_overflow)
+            return c->sticky = fail(c, GX_ERR_NOMEM, "%llu k-mer records overflowed the table and its spill area",
+                                    (unsigned long long)c->h_ctr->table_overflow);
+        const u64 n = c->h_ctr->spill_count;
+        const int old = c->spill_cur;
+        c->spill_cur ^= 1;
+        GX_TRY(set_spill_target(c));   // new spills (from the re-insertion itself) go to the other buffer
+        GX_TRY(grow_table(c));
+        c->ops->insert_records((const u64*)c->spill_keys[old].p, (const unsigned short*)c->spill_meta[old].p, nullptr, n, c->table,
+                               c->capacity, c->d_ctr, c->stream);
+        GX_TRY(check_launch(c, "insert_records"));
+        c->new_key_ratio = -1.0;       // the predictor was wrong: be conservative until re-measured
+        GX_TRY(sync_counters(c));
+    }
+    return GX_OK;
+}
+
 // Insert `n` (key, mask) records that are already grouped by table region (bucket b = records
 // [offsets[b], offsets[b+1])), one launch per region, in groups of regions that fit the table's room.
 int blocked_insert(gx_ctx* c, const u64* keys, const unsigned short* meta, const std::vector<u64>& offsets, u64 distinct) {
@@ -295,7 +365,11 @@ int blocked_insert(gx_ctx* c, const u64* keys, const unsigned short* meta, const
         GX_TRY(reserve_room(c, distinct, max_bucket, offsets[n_buckets], &room));
         u32 e = b;
         u64 group = 0;
-        while (e < n_buckets && (e == b || group + (offsets[e + 1] - offsets[e]) <= room)) { group += offsets[e + 1] - offsets[e]; ++e; }
+        while (e < n_buckets && (e == b || predict_new_keys(c, group + (offsets[e + 1] - offsets[e])) <= room)) {
+            group += offsets[e + 1] - offsets[e];
+            ++e;
+        }
+        c->ratio_pending_occ += group;
         {
             ScopedPhase ph(c, PH_INSERT);
             for (u32 i = b; i < e; ++i) {
@@ -309,7 +383,9 @@ int blocked_insert(gx_ctx* c, const u64* keys, const unsigned short* meta, const
         b = e;
         if (b < n_buckets) {
             GX_TRY(sync_counters(c));
+            GX_TRY(handle_spills(c));
             distinct = c->h_ctr->distinct;
+            note_sync(c, distinct);
         }
     }
     return GX_OK;
@@ -363,7 +439,9 @@ int blocked_chunk(gx_ctx* c, const uint8_t* d_text, size_t n, u64 n_lines, u64 c
 // packed reads and k-mers, then extract + insert.
 int insert_parsed_chunk(gx_ctx* c, const uint8_t* d_text, size_t n) {
     GX_TRY(sync_counters(c));
+    GX_TRY(handle_spills(c));
     const Counters& h = *c->h_ctr;
+    note_sync(c, h.distinct);
     const u64 n_lines = h.chunk_lines;
     c->global_lines += n_lines;
     if (h.error != ~0ull) return line_error_to_status(c, h.error);
@@ -388,12 +466,18 @@ int insert_parsed_chunk(gx_ctx* c, const uint8_t* d_text, size_t n) {
             return blocked_chunk(c, d_text, n, n_lines, h.chunk_occ, n_buckets, distinct);
         }
     }
-    // ---- direct build: extract + upsert, in as many line ranges as the table's room dictates (usually one)
+    // ---- direct build: extract + upsert, in as many line ranges as the table's room and the predictor dictate
     for (u64 line0 = 0; line0 < n_lines;) {
         u64 room = 0;
         GX_TRY(reserve_room(c, distinct, max_line_occ, h.chunk_occ, &room));
-        u64 take = n_lines - line0;
-        if (occ_left > room) take = std::min<u64>(take, std::max<u64>(room / max_line_occ, 1));
+        const u64 lines_left = n_lines - line0;
+        const u64 predicted = predict_new_keys(c, occ_left);
+        u64 take = lines_left;
+        if (predicted > room) {
+            take = (u64)((double)lines_left * (double)room / (double)predicted);
+            take = std::min<u64>(lines_left, std::max<u64>(take, std::max<u64>(room / max_line_occ, 1)));
+        }
+        const u64 take_occ = take == lines_left ? occ_left : std::min<u64>(occ_left, (u64)((double)occ_left * (double)take / (double)lines_left) + max_line_occ);
         ScopedPhase ph(c, PH_INSERT);
         ExtractArgs a{};
         a.text = d_text; a.n_text = n;
@@ -412,16 +496,18 @@ int insert_parsed_chunk(gx_ctx* c, const uint8_t* d_text, size_t n) {
             c->ops->extract_insert(a, c->stream);
             GX_TRY(check_launch(c, "extract_insert"));
         }
+        c->ratio_pending_occ += take_occ;
         line0 += take;
         if (line0 < n_lines) {  // more ranges to go: learn how many keys the last one really added
             GX_TRY(sync_counters(c));
+            GX_TRY(handle_spills(c));
             distinct = c->h_ctr->distinct;
-            occ_left = occ_left > take ? occ_left - take : 0;  // lower bound of what was consumed: every line has >= 1
+            note_sync(c, distinct);
+            occ_left = occ_left > take_occ ? occ_left - take_occ : std::min<u64>(occ_left, (n_lines - line0) * max_line_occ);
         }
     }
     return GX_OK;
 }
-
 
 // Line index of text[0, n): fills *nl_buf with the offsets of the line terminators (virtual one for an unterminated
 // last line) and returns an upper bound of the line count; the exact count is left in Counters::chunk_lines.
@@ -548,7 +634,8 @@ int gx_create(const gx_config* cfg, gx_ctx** out) {
     c->kw = (c->k + 31) / 32;
     c->ops = engine_ops(c->kw);
     if (cfg->reserved[0]) c->chunk_bytes = (size_t)cfg->reserved[0];
-    c->blocked_mode = (int)cfg->reserved[2];
+    c->blocked_mode = (int)(cfg->reserved[2] & 0xff);
+    c->test_no_new_keys = (cfg->reserved[2] >> 8) & 1;  // test hook: predictor claims nothing is new -> exercises spills
     c->blocked_buckets = (u32)std::min<u64>(cfg->reserved[3], MAX_BUCKETS);
     // tuning knob: L2 fetch granularity in bytes (32/64/128); random 16-32 B slot accesses want the smallest
     if (cfg->reserved[1]) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)cfg->reserved[1]);
@@ -558,6 +645,12 @@ int gx_create(const gx_config* cfg, gx_ctx** out) {
     if (cudaMalloc((void**)&c->d_ctr, sizeof(Counters)) != cudaSuccess) return bail(fail(c, GX_ERR_NOMEM, "counters"));
     if (cudaMallocHost((void**)&c->h_ctr, sizeof(Counters)) != cudaSuccess) return bail(fail(c, GX_ERR_NOMEM, "pinned counters"));
     if (c->ops->prepare() != 0) return bail(fail(c, GX_ERR_CUDA, "cudaFuncSetAttribute failed"));
+    c->spill_cap = 4ull << 20;
+    for (int i = 0; i < 2; ++i) {
+        if (ensure(c, c->spill_keys[i], (size_t)c->spill_cap * c->kw * sizeof(u64)) != GX_OK ||
+            ensure(c, c->spill_meta[i], (size_t)c->spill_cap * sizeof(unsigned short)) != GX_OK)
+            return bail(GX_ERR_NOMEM);
+    }
     int r = gx_reset(c);
     if (r != GX_OK) return bail(r);
     *out = c;
@@ -576,6 +669,10 @@ int gx_reset(gx_ctx* c) {
     CUDA_TRY(c, cudaMemcpyAsync(c->d_ctr, c->h_ctr, sizeof z, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     c->table_live = false;  // keep the allocation; it is re-initialised on first use
+    c->new_key_ratio = -1.0;
+    c->ratio_distinct0 = c->ratio_pending_occ = 0;
+    c->spill_cur = 0;
+    GX_TRY(set_spill_target(c));
     GX_TRY(mg_reset(c));
     if (c->heads.p) CUDA_TRY(c, cudaMemsetAsync(c->heads.p, 0, c->heads.cap, c->stream));
     c->grows = 0;
@@ -601,6 +698,7 @@ void gx_destroy(gx_ctx* c) {
                       &c->hperm, &c->tile_bytes, &c->tile_nodes, &c->records, &c->rec_offsets, &c->parts, &c->dense,
                       &c->flat_keys, &c->flat_meta, &c->part_keys, &c->part_meta, &c->bucket_count};
     for (auto* b : bufs) release(*b);
+    for (int i = 0; i < 2; ++i) { release(c->spill_keys[i]); release(c->spill_meta[i]); }
     if (c->table) cudaFree(c->table);
     if (c->d_ctr) cudaFree(c->d_ctr);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
@@ -710,6 +808,7 @@ int gx_finish(gx_ctx* c) {
     cudaSetDevice(c->cfg.device);
     GX_TRY(sync_counters(c));
     if (c->h_ctr->error != ~0ull) return line_error_to_status(c, c->h_ctr->error);
+    GX_TRY(handle_spills(c));
     if (c->cfg.n_ranks > 1) {
         u64 pending = 0;
         GX_TRY(mg_pending(c, &pending));

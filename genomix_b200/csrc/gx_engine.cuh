@@ -128,6 +128,16 @@ __device__ __forceinline__ u32 edge_bit_prev(bool cur_rev, bool prev_rev, u32 a)
     return 1u << (type * 4u + (cur_rev ? 3u - a : a));
 }
 
+// An upsert that ran out of probe budget: park the record; only if even the spill area is full is the job lost.
+template <int KW>
+__device__ __forceinline__ void spill_record(Counters* ctr, const u64 (&key)[KW], u32 mask) {
+    const u64 idx = atomicAdd(&ctr->spill_count, 1ull);
+    if (idx >= ctr->spill_cap) { atomicAdd(&ctr->table_overflow, 1ull); return; }
+#pragma unroll
+    for (int i = 0; i < KW; ++i) ctr->spill_keys[idx * KW + i] = key[i];
+    ctr->spill_meta[idx] = (unsigned short)mask;
+}
+
 // K1 (+K2 when ROUTE == false).
 // Restates ReadsKeyValueParserFactory.SplitReads (:150-196): for every position p of every split mate the
 // forward and reverse-complement k-mers, dir = fwd <= rc ? FORWARD : REVERSE, key = the smaller, one
@@ -141,16 +151,22 @@ template <int KW, int MODE>
 __global__ void __launch_bounds__(EX_THREADS, GX_EX_MIN_BLOCKS) extract_kernel(ExtractArgs a) {
     constexpr bool ROUTE = MODE == EX_ROUTE;
     constexpr bool FLAT = MODE == EX_FLAT;
+    // groups of 30 positions handled per batch: routing batches a whole short read so that one reservation per
+    // (warp, destination) covers up to 120 records; the upsert path batches only in the prefetch variant
+    constexpr int NB = ROUTE ? 4 : (MODE == EX_UPSERT ? EX_BATCH : 1);
+    constexpr bool STASH = NB > 1;
     __shared__ u64 sq[EX_WARPS][WIN_WORDS];
-    // per-lane private stash of a batch's keys and masks (lane-major: conflict-free)
-    __shared__ u64 stash_k[(MODE == EX_UPSERT && EX_BATCH > 1) ? EX_WARPS : 1][EX_BATCH][KW][32];
-    __shared__ unsigned short stash_m[(MODE == EX_UPSERT && EX_BATCH > 1) ? EX_WARPS : 1][EX_BATCH][32];
+    // per-lane private stash of a batch's keys, masks and destinations (lane-major: conflict-free)
+    __shared__ u64 stash_k[STASH ? EX_WARPS : 1][NB][KW][32];
+    __shared__ unsigned short stash_m[STASH ? EX_WARPS : 1][NB][32];
+    __shared__ unsigned short stash_o[(STASH && ROUTE) ? EX_WARPS : 1][NB][32];
     __shared__ u32 bucket_hist[FLAT ? MAX_BUCKETS : 1];  // this CTA's records per table region (EX_FLAT)
     if constexpr (FLAT) {
         for (u32 i = threadIdx.x; i < a.n_buckets; i += EX_THREADS) bucket_hist[i] = 0;
         __syncthreads();
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 lane_lt = (1u << lane) - 1u;
     u64* W = sq[warp];
     uint8_t* Wb = reinterpret_cast<uint8_t*>(W);
     Head<KW>* heads = reinterpret_cast<Head<KW>*>(a.heads);
@@ -181,13 +197,11 @@ __global__ void __launch_bounds__(EX_THREADS, GX_EX_MIN_BLOCKS) extract_kernel(E
                 __syncwarp();
                 for (u32 j = lane; j < nwords; j += 32) Wb[j] = (uint8_t)load_quad(aligned + 4 * j, text_lo, text_hi);
                 __syncwarp();
-                // Groups of 30 positions are handled EX_BATCH at a time: phase A computes every canonical key of the
-                // batch and prefetches its home slot into L2, phase B performs the upserts. Each lane thus keeps up
-                // to EX_BATCH independent table requests in flight instead of one.
-                for (u32 g0 = pa; g0 < pb; g0 += 30 * EX_BATCH) {
-                    u32 acts = 0;
+                for (u32 g0 = pa; g0 < pb; g0 += 30 * NB) {
+                    u32 acts = 0;  // bit j: this lane stashed a record in batch row j
+                    // ---- phase A: canonical key, edge bits, read head; consume or stash
 #pragma unroll
-                    for (int j = 0; j < EX_BATCH; ++j) {
+                    for (int j = 0; j < NB; ++j) {
                         const u32 g = g0 + 30 * j;
                         if (g >= pb) break;  // warp-uniform
                         const long long p = (long long)g - 1 + lane;
@@ -201,98 +215,103 @@ __global__ void __launch_bounds__(EX_THREADS, GX_EX_MIN_BLOCKS) extract_kernel(E
                         }
                         const u32 dirs = __ballot_sync(0xffffffffu, comp && rev);
                         const bool active = lane >= 1 && lane <= 30 && p < (long long)pb;
-                        u32 route_dest = 0xffffffffu, route_mask = 0;
-                        u64 route_key[KW];
-                        (void)route_mask; (void)route_key;
-                        if (active) {
-                            u32 mask = 0;
-                            if (p + 1 < (long long)npos)
-                                mask |= edge_bit_next(rev, (dirs >> (lane + 1)) & 1u, window_letter(W, (u32)(p + k - lo) + m));
-                            if (p > 0)
-                                mask |= edge_bit_prev(rev, (dirs >> (lane - 1)) & 1u, window_letter(W, (u32)(p - 1 - lo) + m));
-                            u64 key[KW];
+                        if (!active) continue;
+                        u32 mask = 0;
+                        if (p + 1 < (long long)npos)
+                            mask |= edge_bit_next(rev, (dirs >> (lane + 1)) & 1u, window_letter(W, (u32)(p + k - lo) + m));
+                        if (p > 0)
+                            mask |= edge_bit_prev(rev, (dirs >> (lane - 1)) & 1u, window_letter(W, (u32)(p - 1 - lo) + m));
+                        u64 key[KW];
 #pragma unroll
-                            for (int i = 0; i < KW; ++i) key[i] = rev ? rc[i] : f[i];
-                            if (p == 0) {
-                                Head<KW>& h = heads[d.head_idx[mate]];
+                        for (int i = 0; i < KW; ++i) key[i] = rev ? rc[i] : f[i];
+                        if (p == 0) {
+                            Head<KW>& h = heads[d.head_idx[mate]];
 #pragma unroll
-                                for (int i = 0; i < KW; ++i) h.key[i] = key[i];
-                                // offset 0 unflipped, K-1 flipped (:165-170); library always 0 (:98-106)
-                                h.uuid = (rev ? ((u64)(k - 1) << 40) : 0ull) | ((u64)mate << 35) | d.read_id;
-                                h.this_off = d.store[mate];
-                                h.mate_off = d.store[1 - mate];
-                                h.this_len = len;
-                                h.mate_len = d.len[1 - mate];
-                                h.flipped = rev ? 1u : 0u;
-                                h.valid = 1u;
-                            }
-                            if constexpr (FLAT) {
-                                // L2-blocked build, pass 1: the occurrence goes to its flat slot (no atomics: the parser
-                                // reserved [occ_base, occ_base + positions) for this line) and its table region is counted
-                                const u64 idx = d.occ_base + (mate && (d.flags & 1u) ? (u64)(d.len[0] - (u32)k + 1u) : 0ull) + (u64)p;
-#pragma unroll
-                                for (int i = 0; i < KW; ++i) a.flat_keys[idx * KW + i] = key[i];
-                                a.flat_meta[idx] = (unsigned short)mask;
-                                atomicAdd(&bucket_hist[bucket_of(hash_key<KW>(key), a.n_buckets)], 1u);
-                            } else if constexpr (!ROUTE) {
-                                if constexpr (EX_BATCH == 1) {
-                                    bool is_new;
-                                    if (table_upsert<KW>(a.table, a.capacity, key, 1ull, mask, is_new) == a.capacity)
-                                        atomicAdd(&a.ctr->table_overflow, 1ull);
-                                    new_slots += is_new ? 1u : 0u;
-                                } else {
-#pragma unroll
-                                    for (int i = 0; i < KW; ++i) stash_k[warp][j][i][lane] = key[i];
-                                    stash_m[warp][j][lane] = (unsigned short)mask;
-                                    prefetch_l2(a.table + slot_of(hash_key<KW>(key), a.capacity) * SlotTraits<KW>::WORDS);
-                                    acts |= 1u << j;
-                                }
-                            } else {
-                                // multi-GPU: own keys go straight into the table, the others are appended to their
-                                // owner's send bucket (one atomic per warp and destination)
-                                const u32 owner = owner_of(hash_key<KW>(key), a.n_ranks);
-                                route_dest = owner;
-                                if (owner == a.rank) {
-                                    bool is_new;
-                                    if (table_upsert<KW>(a.table, a.capacity, key, 1ull, mask, is_new) == a.capacity)
-                                        atomicAdd(&a.ctr->table_overflow, 1ull);
-                                    new_slots += is_new ? 1u : 0u;
-                                    route_dest = 0xffffffffu;
-                                } else {
-#pragma unroll
-                                    for (int i = 0; i < KW; ++i) route_key[i] = key[i];
-                                    route_mask = mask;
-                                }
-                            }
+                            for (int i = 0; i < KW; ++i) h.key[i] = key[i];
+                            // offset 0 unflipped, K-1 flipped (:165-170); library always 0 (:98-106)
+                            h.uuid = (rev ? ((u64)(k - 1) << 40) : 0ull) | ((u64)mate << 35) | d.read_id;
+                            h.this_off = d.store[mate];
+                            h.mate_off = d.store[1 - mate];
+                            h.this_len = len;
+                            h.mate_len = d.len[1 - mate];
+                            h.flipped = rev ? 1u : 0u;
+                            h.valid = 1u;
                         }
-                        if constexpr (ROUTE) {
-                            // warp-aggregated append: lanes with the same destination share one reservation
-                            const u32 live = __ballot_sync(0xffffffffu, route_dest != 0xffffffffu);
-                            if (route_dest != 0xffffffffu) {
-                                const u32 peers = __match_any_sync(live, route_dest);
-                                const int leader = __ffs(peers) - 1;
-                                u64 base = 0;
-                                if (lane == leader) base = atomicAdd(a.route_count + route_dest, (u64)__popc(peers));
-                                base = __shfl_sync(peers, base, leader);
-                                const u64 idx = base + __popc(peers & ((1u << lane) - 1u));
-                                u64* kd = a.route_keys[route_dest] + idx * KW;
+                        if constexpr (FLAT) {
+                            // L2-blocked build, pass 1: the occurrence goes to its flat slot (no atomics: the parser
+                            // reserved [occ_base, occ_base + positions) for this line) and its table region is counted
+                            const u64 idx = d.occ_base + (mate && (d.flags & 1u) ? (u64)(d.len[0] - (u32)k + 1u) : 0ull) + (u64)p;
 #pragma unroll
-                                for (int i = 0; i < KW; ++i) kd[i] = route_key[i];
-                                a.route_meta[route_dest][idx] = (unsigned short)route_mask;
+                            for (int i = 0; i < KW; ++i) a.flat_keys[idx * KW + i] = key[i];
+                            a.flat_meta[idx] = (unsigned short)mask;
+                            atomicAdd(&bucket_hist[bucket_of(hash_key<KW>(key), a.n_buckets)], 1u);
+                        } else {
+                            bool direct = !STASH;
+                            if constexpr (ROUTE) {
+                                // multi-GPU: own keys go straight into the table, the others wait for phase B
+                                const u32 owner = owner_of(hash_key<KW>(key), a.n_ranks);
+                                direct = owner == a.rank;
+                                if (!direct) stash_o[warp][j][lane] = (unsigned short)owner;
+                            }
+                            if (direct) {
+                                bool is_new;
+                                if (table_upsert<KW>(a.table, a.capacity, key, 1ull, mask, is_new) == a.capacity)
+                                    spill_record<KW>(a.ctr, key, mask);
+                                new_slots += is_new ? 1u : 0u;
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < KW; ++i) stash_k[warp][j][i][lane] = key[i];
+                                stash_m[warp][j][lane] = (unsigned short)mask;
+                                if constexpr (!ROUTE)
+                                    prefetch_l2(a.table + slot_of(hash_key<KW>(key), a.capacity) * SlotTraits<KW>::WORDS);
+                                acts |= 1u << j;
                             }
                         }
                     }
-                    if constexpr (MODE == EX_UPSERT && EX_BATCH > 1) {
+                    // ---- phase B
+                    if constexpr (STASH && !ROUTE) {  // prefetch variant: the upserts, now (mostly) L2 hits
 #pragma unroll
-                        for (int j = 0; j < EX_BATCH; ++j) {
+                        for (int j = 0; j < NB; ++j) {
                             if (!((acts >> j) & 1u)) continue;
                             u64 key[KW];
 #pragma unroll
                             for (int i = 0; i < KW; ++i) key[i] = stash_k[warp][j][i][lane];
                             bool is_new;
                             if (table_upsert<KW>(a.table, a.capacity, key, 1ull, stash_m[warp][j][lane], is_new) == a.capacity)
-                                atomicAdd(&a.ctr->table_overflow, 1ull);
+                                spill_record<KW>(a.ctr, key, stash_m[warp][j][lane]);
                             new_slots += is_new ? 1u : 0u;
+                        }
+                    }
+                    if constexpr (ROUTE) {
+                        // append the batch to the owners' send buckets: per destination one reservation for the whole
+                        // warp (ballot counts), then every lane writes its records at base + rank
+                        if (__any_sync(0xffffffffu, acts != 0)) {
+                            for (u32 dest = 0; dest < a.n_ranks; ++dest) {
+                                if (dest == a.rank) continue;
+                                u32 mine[NB];
+                                u32 total = 0;
+#pragma unroll
+                                for (int j = 0; j < NB; ++j) {
+                                    mine[j] = __ballot_sync(0xffffffffu, ((acts >> j) & 1u) && stash_o[warp][j][lane] == dest);
+                                    total += __popc(mine[j]);
+                                }
+                                if (total == 0) continue;
+                                u64 base = 0;
+                                if (lane == 0) base = atomicAdd(a.route_count + dest, (u64)total);
+                                base = __shfl_sync(0xffffffffu, base, 0);
+                                u64* kbase = a.route_keys[dest];
+                                unsigned short* mbase = a.route_meta[dest];
+#pragma unroll
+                                for (int j = 0; j < NB; ++j) {
+                                    if ((mine[j] >> lane) & 1u) {
+                                        const u64 idx = base + __popc(mine[j] & lane_lt);
+#pragma unroll
+                                        for (int i = 0; i < KW; ++i) kbase[idx * KW + i] = stash_k[warp][j][i][lane];
+                                        mbase[idx] = stash_m[warp][j][lane];
+                                    }
+                                    base += __popc(mine[j]);
+                                }
+                            }
                         }
                     }
                 }
@@ -322,7 +341,7 @@ __global__ void __launch_bounds__(256) insert_records_kernel(const u64* __restri
         for (int j = 0; j < KW; ++j) key[j] = keys[i * KW + j];
         bool is_new;
         if (table_upsert<KW>(table, capacity, key, counts ? (u64)counts[i] : 1ull, meta[i], is_new) == capacity)
-            atomicAdd(&ctr->table_overflow, 1ull);
+            spill_record<KW>(ctr, key, meta[i]);
         new_slots += is_new ? 1u : 0u;
     }
 #pragma unroll
@@ -720,9 +739,10 @@ __device__ void serialise_node(const EmitArgs& a, u64 slot, const u64 (&key)[KW]
         const u32 bits = (mask >> (4 * t)) & 0xfu;
         if (!bits) continue;
         w.put32be((u32)__popc(bits));
-#pragma unroll
-        for (u32 b = 0; b < 4; ++b) {
-            if (!((bits >> b) & 1u)) continue;
+        // walk the set bits (not all four bases): lanes of a warp stay converged on "my next edge of this type"
+#pragma unroll 1
+        for (u32 rest = bits; rest; rest &= rest - 1u) {
+            const u32 b = (u32)__ffs(rest) - 1u;
             u64 nk[KW];
             if (t == 0) key_append<KW>(key, a.k, b, nk);
             else if (t == 1) key_prepend<KW>(rcx, a.k, 3u - b, nk);

@@ -148,6 +148,8 @@ int gx_mg_exchange(gx_ctx* c) {
     cudaSetDevice(c->cfg.device);
     const int n = m->n, me = m->rank;
     GX_TRY(sync_counters(c));
+    GX_TRY(handle_spills(c));
+    note_sync(c, c->h_ctr->distinct);
     const u64 head_cursor = c->h_ctr->head_cursor, store_cursor = c->h_ctr->store_cursor;
     ScopedPhase ph(c, PH_EXCHANGE);
     // ---- 1. bucket the read heads created since the last exchange
@@ -220,14 +222,19 @@ int gx_mg_exchange(gx_ctx* c) {
         for (u64 done = 0; done < recv_kmers;) {
             u64 room = 0;
             GX_TRY(reserve_room(c, distinct, 1, recv_kmers, &room));
-            const u64 take = std::min<u64>(recv_kmers - done, room);
+            u64 take = recv_kmers - done;
+            const u64 predicted = predict_new_keys(c, take);
+            if (predicted > room) take = std::max<u64>(std::min<u64>(take, room), (u64)((double)take * (double)room / (double)predicted));
+            c->ratio_pending_occ += take;
             c->ops->insert_records((const u64*)m->recv_keys.p + done * c->kw, (const unsigned short*)m->recv_meta.p + done, nullptr,
                                    take, c->table, c->capacity, c->d_ctr, c->stream);
             GX_TRY(check_launch(c, "insert_records"));
             done += take;
             if (done < recv_kmers) {
                 GX_TRY(sync_counters(c));
+                GX_TRY(handle_spills(c));
                 distinct = c->h_ctr->distinct;
+                note_sync(c, distinct);
             }
         }
     }

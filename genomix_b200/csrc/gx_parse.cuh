@@ -26,6 +26,12 @@ struct Counters {
     u64 read_heads;      // ReadHeadInfo entries after de-duplication
     u64 table_overflow;  // upserts that ran out of probe budget (must stay 0)
     u64 chunk_max_line_occ;  // largest k-mer occurrence count of one line in the current chunk
+    // spill area: (key, mask) records whose upsert ran out of probe budget because the table filled up faster than
+    // the host predicted; the host grows the table and inserts them afterwards (gx_api.cu handle_spills)
+    u64 spill_count;
+    u64 spill_cap;
+    u64* spill_keys;
+    unsigned short* spill_meta;
     u64 scratch[2];
 };
 

@@ -64,10 +64,11 @@ __device__ __forceinline__ void fold_value(u64* val, u64 add, u32 mask, u64 seen
 }
 
 // Insert-or-aggregate. Returns the slot index; *is_new set when this call created the slot.
-// A probe budget guards against a full table or a protocol bug turning into a hung GPU: the host keeps the
-// load factor below GROW_LOAD, so the budget is never reached in a correct run; if it is, `capacity` is
-// returned and the caller raises Counters::table_overflow (the job then fails loudly).
-static constexpr u64 PROBE_BUDGET = 1ull << 24;
+// A probe budget bounds the work of one upsert: the host sizes batches so that the load stays near GROW_LOAD, where
+// probe sequences are a handful of slots; if its prediction of new keys was too low and the table fills up, the
+// budget runs out, `capacity` is returned and the caller spills the record (spill_record) for the host to insert
+// after growing the table. Never a hang, never a lost occurrence.
+static constexpr u64 PROBE_BUDGET = 1ull << 14;
 
 template <int KW>
 __device__ __forceinline__ u64 table_upsert(u64* __restrict__ table, u64 capacity, const u64 (&key)[KW], u64 add,

@@ -19,6 +19,13 @@ def oracle_canonical(k, text):
     return {key: T.Node.read(val, 0)[0].canonical_bytes() for key, val in recs.items()}
 
 
+def oracle_canonical_c(k, text):
+    """same as oracle_canonical through the C twin (for inputs too large for the pure-Python oracle)"""
+    from genomix_b200 import types as T
+    from oracle import c_oracle as CO
+    return T.canonical_records(CO.build_graph_records(k, text, 4)[0])
+
+
 def gpu_canonical(k, text, **kw):
     gx = _gx()
     stream = gx.build_graph(k, text, **kw)
@@ -119,6 +126,22 @@ def test_table_growth_rehash():
         gb.push_lines(text)
         gb.finish()
         assert gb.stats()["table_grows"] >= 1
+        assert gx.types.canonical_records(gb.records()) == want
+
+
+@pytest.mark.parametrize("k", [21, 55, 91])
+def test_spill_and_regrow_when_the_predictor_is_wrong(k):
+    """test hook (reserved[2] bit 8): the host assumes no occurrence is a new key, so the tiny initial table fills up
+    completely, upserts run out of probe budget, spill, and are re-inserted after the table has grown"""
+    gx = _gx()
+    rng = np.random.default_rng(77 + k)
+    text = random_reads_text(rng, 4000, k + 20, k + 80, genome_len=400000)
+    want = oracle_canonical_c(k, text)
+    with gx.GraphBuilder(k, blocked_mode=1 | 256, expected_kmers=1000) as gb:   # 65536-slot table, ~190k distinct keys
+        gb.push_lines(text)
+        gb.finish()
+        st = gb.stats()
+        assert st["table_grows"] >= 1
         assert gx.types.canonical_records(gb.records()) == want
 
 
