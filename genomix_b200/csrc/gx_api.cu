@@ -47,7 +47,7 @@ struct DevBuf {
     size_t cap = 0;
 };
 
-enum Phase { PH_PARSE = 0, PH_INSERT = 1, PH_EXCHANGE = 2, PH_FINISH = 3, PH_H2D = 4, PH_COUNT = 8 };
+enum Phase { PH_PARSE = 0, PH_INSERT = 1, PH_EXCHANGE = 2, PH_FINISH = 3, PH_H2D = 4, PH_XCOMM = 5, PH_XINSERT = 6, PH_COUNT = 8 };
 
 struct PendingTimer {
     int phase;

@@ -1,4 +1,5 @@
 // gx_kw.inl -- instantiates the engine for one key width; included by gx_kw<N>.cu with GX_KW defined.
+#include <algorithm>
 #include "gx_engine.cuh"
 
 namespace gx {
@@ -26,7 +27,8 @@ void l_partition_flat(const u64* flat_keys, const unsigned short* flat_meta, u64
 void l_insert_records(const u64* keys, const unsigned short* meta, const u32* counts, u64 n, u64* table, u64 capacity,
                       Counters* ctr, cudaStream_t st) {
     if (n == 0) return;
-    insert_records_kernel<KW><<<grid_for(n, 256, 148 * 8), 256, 0, st>>>(keys, meta, counts, n, table, capacity, ctr);
+    // short-lived CTAs (4 records per thread) so that concurrent kernels of other streams (NCCL) get SM slots promptly
+    insert_records_kernel<KW><<<(unsigned)std::min<u64>((n + 1023) / 1024, 1u << 30), 256, 0, st>>>(keys, meta, counts, n, table, capacity, ctr);
 }
 void l_rehash(const u64* old_table, u64 old_capacity, u64* table, u64 capacity, cudaStream_t st) {
     rehash_kernel<KW><<<grid_for(old_capacity, 256, 148 * 8), 256, 0, st>>>(old_table, old_capacity, table, capacity);

@@ -24,10 +24,17 @@ struct MgState {
     DevBuf ptr_table;      // device copy of the 4 pointer arrays: [4][n]
     DevBuf counts;         // device u64 [3n]: kmer records, heads, store bytes per destination
     DevBuf all_counts;     // device u64 [n][3n] after the all-gather
-    DevBuf recv_keys, recv_meta;
+    DevBuf inbox[4];       // receive areas: key words, masks, Head<KW> records, packed sequences
+    bool use_ipc = true;   // deliver with copy engines into CUDA-IPC mapped peer inboxes (else ncclSend/ncclRecv)
+    std::vector<size_t> pub_cap;   // [n][4] inbox capacities every rank has published
+    std::vector<void*> peer_ptr;   // [n][4] peers' inboxes mapped into this process
+    DevBuf pub_dev, token;
     std::vector<u64> h_counts;  // host copy of counts (valid after a sync)
     u64 routed_heads_upto = 0, routed_store_upto = 0;
     u64 exchanged = 0;
+    cudaStream_t comm_stream = nullptr;   // NCCL traffic runs here, overlapped with the upserts on the ctx stream
+    cudaEvent_t ev_ready = nullptr;
+    std::vector<cudaEvent_t> ev_step;
 };
 
 MgState* mg_of(gx_ctx* c) { return reinterpret_cast<MgState*>(c->mg); }
@@ -90,10 +97,16 @@ u64 mg_exchanged(gx_ctx* c) { return mg_of(c) ? mg_of(c)->exchanged : 0; }
 void mg_destroy(gx_ctx* c) {
     MgState* m = mg_of(c);
     if (!m) return;
+    if (m->comm_stream) cudaStreamSynchronize(m->comm_stream);
     if (m->comm) ncclCommDestroy(m->comm);
+    if (m->comm_stream) cudaStreamDestroy(m->comm_stream);
+    if (m->ev_ready) cudaEventDestroy(m->ev_ready);
+    for (auto e : m->ev_step) if (e) cudaEventDestroy(e);
     for (auto* v : {&m->route_keys, &m->route_meta, &m->send_heads, &m->send_store})
         for (auto& b : *v) release(b);
-    release(m->ptr_table); release(m->counts); release(m->all_counts); release(m->recv_keys); release(m->recv_meta);
+    for (void* mp : m->peer_ptr) if (mp) cudaIpcCloseMemHandle(mp);
+    release(m->ptr_table); release(m->counts); release(m->all_counts); release(m->pub_dev); release(m->token);
+    for (auto& b : m->inbox) release(b);
     delete m;
     c->mg = nullptr;
 }
@@ -132,9 +145,21 @@ int gx_mg_init(gx_ctx* c, const uint8_t id_bytes[128]) {
     ncclUniqueId id;
     memcpy(&id, id_bytes, 128);
     NCCL_TRY(c, ncclCommInitRank(&m->comm, m->n, id, m->rank));
+    {   // highest priority: NCCL's copy CTAs get the next free SM slots while the upsert kernel is running
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        CUDA_TRY(c, cudaStreamCreateWithPriority(&m->comm_stream, cudaStreamNonBlocking, hi));
+    }
+    CUDA_TRY(c, cudaEventCreateWithFlags(&m->ev_ready, cudaEventDisableTiming));
+    m->ev_step.resize(m->n);
+    for (auto& e : m->ev_step) CUDA_TRY(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     GX_TRY(ensure(c, m->ptr_table, (size_t)4 * m->n * sizeof(void*)));
     GX_TRY(ensure(c, m->counts, (size_t)3 * m->n * sizeof(u64)));
     GX_TRY(ensure(c, m->all_counts, (size_t)3 * m->n * m->n * sizeof(u64)));
+    GX_TRY(ensure(c, m->token, 256, 0, true));
+    m->pub_cap.assign((size_t)m->n * 4, 0);
+    m->peer_ptr.assign((size_t)m->n * 4, nullptr);
+    m->use_ipc = getenv("GENOMIX_GB_NO_IPC") == nullptr;
     CUDA_TRY(c, cudaMemsetAsync(m->counts.p, 0, (size_t)3 * m->n * sizeof(u64), c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return GX_OK;
@@ -185,79 +210,171 @@ int gx_mg_exchange(gx_ctx* c) {
         if (s == me) continue;
         recv_kmers += cnt(s, 0, me); recv_heads += cnt(s, 1, me); recv_store += cnt(s, 2, me);
     }
-    // ---- 3. room for what arrives
-    GX_TRY(ensure(c, m->recv_keys, (size_t)std::max<u64>(recv_kmers, 1) * c->kw * sizeof(u64)));
-    GX_TRY(ensure(c, m->recv_meta, (size_t)std::max<u64>(recv_kmers, 1) * sizeof(unsigned short)));
+    // ---- 3. inboxes. Every rank knows every rank's needs (the count matrix is global), so all ranks take the same
+    //         decision about who has to (re)allocate: mappings of a growing inbox are closed everywhere, a barrier lets
+    //         its owner reallocate, new CUDA-IPC handles are published and opened. Steady state: nothing to do.
+    auto unit_bytes = [&](int kind) -> size_t {
+        return kind == 0 ? (size_t)c->kw * sizeof(u64) : kind == 1 ? sizeof(unsigned short) : kind == 2 ? c->ops->head_bytes : 1;
+    };
+    auto count_kind = [&](int src, int kind, int dst) { return cnt(src, kind == 0 || kind == 1 ? 0 : kind - 1, dst); };
+    auto need_bytes = [&](int dst, int kind) {
+        u64 tot = 0;
+        for (int s2 = 0; s2 < n; ++s2) if (s2 != dst) tot += count_kind(s2, kind, dst);
+        return (size_t)tot * unit_bytes(kind);
+    };
+    if (m->use_ipc) {
+        bool any_grow = false;
+        std::vector<char> grows(n, 0);
+        for (int p = 0; p < n; ++p)
+            for (int kind = 0; kind < 4; ++kind)
+                if (need_bytes(p, kind) > m->pub_cap[(size_t)p * 4 + kind]) { grows[p] = 1; any_grow = true; }
+        if (any_grow) {
+            for (int p = 0; p < n; ++p) {
+                if (!grows[p] || p == me) continue;
+                for (int kind = 0; kind < 4; ++kind) {
+                    void*& mp = m->peer_ptr[(size_t)p * 4 + kind];
+                    if (mp) { cudaIpcCloseMemHandle(mp); mp = nullptr; }
+                }
+            }
+            NCCL_TRY(c, ncclAllReduce(m->token.p, m->token.p, 1, ncclFloat, ncclSum, m->comm, c->stream));  // everyone closed
+            CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+            struct Pub { cudaIpcMemHandle_t h[4]; u64 cap[4]; };
+            Pub mine;
+            memset(&mine, 0, sizeof mine);
+            for (int kind = 0; kind < 4; ++kind) {
+                if (grows[me]) {
+                    const size_t want = std::max<size_t>(need_bytes(me, kind) + need_bytes(me, kind) / 4 + 4096, 2 * m->inbox[kind].cap);
+                    if (need_bytes(me, kind) > m->inbox[kind].cap) {
+                        release(m->inbox[kind]);
+                        GX_TRY(ensure(c, m->inbox[kind], want));
+                    }
+                }
+                mine.cap[kind] = m->inbox[kind].cap;
+                if (m->inbox[kind].p && cudaIpcGetMemHandle(&mine.h[kind], m->inbox[kind].p) != cudaSuccess) {
+                    cudaGetLastError();
+                    return fail(c, GX_ERR_CUDA, "cudaIpcGetMemHandle failed (set GENOMIX_GB_NO_IPC=1 to use NCCL send/recv)");
+                }
+            }
+            GX_TRY(ensure(c, m->pub_dev, sizeof(Pub) * (size_t)(n + 1)));
+            CUDA_TRY(c, cudaMemcpyAsync(m->pub_dev.p, &mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
+            NCCL_TRY(c, ncclAllGather(m->pub_dev.p, (uint8_t*)m->pub_dev.p + sizeof(Pub), sizeof(Pub), ncclUint8, m->comm, c->stream));
+            std::vector<Pub> pubs(n);
+            CUDA_TRY(c, cudaMemcpyAsync(pubs.data(), (uint8_t*)m->pub_dev.p + sizeof(Pub), sizeof(Pub) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+            for (int p = 0; p < n; ++p) {
+                for (int kind = 0; kind < 4; ++kind) {
+                    m->pub_cap[(size_t)p * 4 + kind] = pubs[p].cap[kind];
+                    if (p == me || !grows[p] || pubs[p].cap[kind] == 0) continue;
+                    void* mp = nullptr;
+                    if (cudaIpcOpenMemHandle(&mp, pubs[p].h[kind], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                        cudaGetLastError();
+                        return fail(c, GX_ERR_CUDA, "cudaIpcOpenMemHandle failed for rank %d (set GENOMIX_GB_NO_IPC=1 to use NCCL send/recv)", p);
+                    }
+                    m->peer_ptr[(size_t)p * 4 + kind] = mp;
+                }
+            }
+        }
+    } else {
+        for (int kind = 0; kind < 4; ++kind) GX_TRY(ensure(c, m->inbox[kind], std::max<size_t>(need_bytes(me, kind), 1)));
+    }
     GX_TRY(ensure(c, c->heads, (size_t)(head_cursor + recv_heads) * c->ops->head_bytes, (size_t)head_cursor * c->ops->head_bytes, true));
     GX_TRY(ensure(c, c->store, (size_t)(store_cursor + recv_store), (size_t)store_cursor));
-    // ---- 4. all-to-all-v over NVLink
-    NCCL_TRY(c, ncclGroupStart());
-    {
-        u64 rk = 0, rh = 0, rs = 0;
-        for (int p = 0; p < n; ++p) {
-            if (p == me) continue;
-            const u64 sk = cnt(me, 0, p), sh = cnt(me, 1, p), ss = cnt(me, 2, p);
-            if (sk) {
-                NCCL_TRY(c, ncclSend(m->route_keys[p].p, (size_t)sk * c->kw, ncclUint64, p, m->comm, c->stream));
-                NCCL_TRY(c, ncclSend(m->route_meta[p].p, (size_t)sk * 2, ncclUint8, p, m->comm, c->stream));
+    // offset (in units) of source s's segment inside rank dst's inbox of a kind: sources are laid out in rank order
+    auto seg_off = [&](int s2, int kind, int dst) {
+        u64 off = 0;
+        for (int q = 0; q < s2; ++q) if (q != dst) off += count_kind(q, kind, dst);
+        return off;
+    };
+    // ---- 4. all-to-all-v over NVLink in n-1 ring-shift steps on a communication stream: in step i every rank delivers
+    //         to (me+i) and is delivered to by (me-i). With CUDA IPC the delivery is a copy-engine push straight into the
+    //         peer's inbox (no SMs involved) followed by a tiny all-reduce as arrival barrier; without, ncclSend/ncclRecv.
+    //         The segment that arrived in step i is upserted on the compute stream while step i+1 is on the wire.
+    CUDA_TRY(c, cudaEventRecord(m->ev_ready, c->stream));
+    CUDA_TRY(c, cudaStreamWaitEvent(m->comm_stream, m->ev_ready, 0));
+    PendingTimer comm_t{PH_XCOMM, get_event(c), get_event(c)};
+    cudaEventRecord(comm_t.a, m->comm_stream);
+    for (int i = 1; i < n; ++i) {
+        const int to = (me + i) % n, from = (me - i + n) % n;
+        const void* src[4] = {m->route_keys[to].p, m->route_meta[to].p, m->send_heads[to].p, m->send_store[to].p};
+        if (m->use_ipc) {
+            for (int kind = 0; kind < 4; ++kind) {
+                const size_t bytes = (size_t)count_kind(me, kind, to) * unit_bytes(kind);
+                if (!bytes) continue;
+                uint8_t* dst = (uint8_t*)m->peer_ptr[(size_t)to * 4 + kind] + (size_t)seg_off(me, kind, to) * unit_bytes(kind);
+                CUDA_TRY(c, cudaMemcpyAsync(dst, src[kind], bytes, cudaMemcpyDeviceToDevice, m->comm_stream));
             }
-            if (sh) NCCL_TRY(c, ncclSend(m->send_heads[p].p, (size_t)sh * c->ops->head_bytes, ncclUint8, p, m->comm, c->stream));
-            if (ss) NCCL_TRY(c, ncclSend(m->send_store[p].p, (size_t)ss, ncclUint8, p, m->comm, c->stream));
-            const u64 gk = cnt(p, 0, me), gh = cnt(p, 1, me), gs = cnt(p, 2, me);
-            if (gk) {
-                NCCL_TRY(c, ncclRecv((u64*)m->recv_keys.p + rk * c->kw, (size_t)gk * c->kw, ncclUint64, p, m->comm, c->stream));
-                NCCL_TRY(c, ncclRecv((unsigned short*)m->recv_meta.p + rk, (size_t)gk * 2, ncclUint8, p, m->comm, c->stream));
+            NCCL_TRY(c, ncclAllReduce(m->token.p, m->token.p, 1, ncclFloat, ncclSum, m->comm, m->comm_stream));
+        } else {
+            NCCL_TRY(c, ncclGroupStart());
+            for (int kind = 0; kind < 4; ++kind) {
+                const size_t sb = (size_t)count_kind(me, kind, to) * unit_bytes(kind);
+                if (sb) NCCL_TRY(c, ncclSend(src[kind], sb, ncclUint8, to, m->comm, m->comm_stream));
+                const size_t rb = (size_t)count_kind(from, kind, me) * unit_bytes(kind);
+                if (rb) NCCL_TRY(c, ncclRecv((uint8_t*)m->inbox[kind].p + (size_t)seg_off(from, kind, me) * unit_bytes(kind), rb, ncclUint8,
+                                             from, m->comm, m->comm_stream));
             }
-            if (gh) NCCL_TRY(c, ncclRecv((uint8_t*)c->heads.p + (size_t)(head_cursor + rh) * c->ops->head_bytes,
-                                         (size_t)gh * c->ops->head_bytes, ncclUint8, p, m->comm, c->stream));
-            if (gs) NCCL_TRY(c, ncclRecv((uint8_t*)c->store.p + store_cursor + rs, (size_t)gs, ncclUint8, p, m->comm, c->stream));
-            rk += gk; rh += gh; rs += gs;
-            m->exchanged += sk;
+            NCCL_TRY(c, ncclGroupEnd());
         }
+        CUDA_TRY(c, cudaEventRecord(m->ev_step[i], m->comm_stream));
+        m->exchanged += cnt(me, 0, to);
     }
-    NCCL_TRY(c, ncclGroupEnd());
-    // ---- 5. fold what arrived
+    cudaEventRecord(comm_t.b, m->comm_stream);
+    c->timers.push_back(comm_t);
+    // ---- 5. fold what arrives, segment by segment
     {
+        ScopedPhase phi(c, PH_XINSERT);
         u64 distinct = c->h_ctr->distinct;
-        for (u64 done = 0; done < recv_kmers;) {
-            u64 room = 0;
-            GX_TRY(reserve_room(c, distinct, 1, recv_kmers, &room));
-            u64 take = recv_kmers - done;
-            const u64 predicted = predict_new_keys(c, take);
-            if (predicted > room) take = std::max<u64>(std::min<u64>(take, room), (u64)((double)take * (double)room / (double)predicted));
-            c->ratio_pending_occ += take;
-            c->ops->insert_records((const u64*)m->recv_keys.p + done * c->kw, (const unsigned short*)m->recv_meta.p + done, nullptr,
-                                   take, c->table, c->capacity, c->d_ctr, c->stream);
-            GX_TRY(check_launch(c, "insert_records"));
-            done += take;
-            if (done < recv_kmers) {
-                GX_TRY(sync_counters(c));
-                GX_TRY(handle_spills(c));
-                distinct = c->h_ctr->distinct;
-                note_sync(c, distinct);
+        for (int i = 1; i < n; ++i) {
+            const int from = (me - i + n) % n;
+            CUDA_TRY(c, cudaStreamWaitEvent(c->stream, m->ev_step[i], 0));
+            const u64 gk = cnt(from, 0, me), base = seg_off(from, 0, me);
+            for (u64 done = 0; done < gk;) {
+                u64 room = 0;
+                GX_TRY(reserve_room(c, distinct, 1, recv_kmers, &room));
+                u64 take = gk - done;
+                const u64 predicted = predict_new_keys(c, take);
+                if (predicted > room) take = std::max<u64>(std::min<u64>(take, room), (u64)((double)take * (double)room / (double)predicted));
+                c->ratio_pending_occ += take;
+                c->ops->insert_records((const u64*)m->inbox[0].p + (base + done) * c->kw, (const unsigned short*)m->inbox[1].p + base + done,
+                                       nullptr, take, c->table, c->capacity, c->d_ctr, c->stream);
+                GX_TRY(check_launch(c, "insert_records"));
+                done += take;
+                if (done < gk) {
+                    GX_TRY(sync_counters(c));
+                    GX_TRY(handle_spills(c));
+                    distinct = c->h_ctr->distinct;
+                    note_sync(c, distinct);
+                }
             }
         }
     }
-    {
-        u64 rh = 0, rs = 0;
+    // ---- 6. received read heads and their sequences join the local arrays (all steps have been waited for above)
+    if (recv_heads) {
+        CUDA_TRY(c, cudaMemcpyAsync((uint8_t*)c->heads.p + (size_t)head_cursor * c->ops->head_bytes, m->inbox[2].p,
+                                    (size_t)recv_heads * c->ops->head_bytes, cudaMemcpyDeviceToDevice, c->stream));
+        if (recv_store)
+            CUDA_TRY(c, cudaMemcpyAsync((uint8_t*)c->store.p + store_cursor, m->inbox[3].p, (size_t)recv_store, cudaMemcpyDeviceToDevice, c->stream));
         for (int p = 0; p < n; ++p) {
             if (p == me) continue;
-            const u64 gh = cnt(p, 1, me), gs = cnt(p, 2, me);
-            if (gh) {
-                c->ops->rebase_heads(c->heads.p, head_cursor + rh, gh, store_cursor + rs, c->stream);
-                GX_TRY(check_launch(c, "rebase_heads"));
-            }
-            rh += gh; rs += gs;
+            const u64 gh = cnt(p, 1, me);
+            if (!gh) continue;
+            c->ops->rebase_heads(c->heads.p, head_cursor + seg_off(p, 2, me), gh, store_cursor + seg_off(p, 3, me), c->stream);
+            GX_TRY(check_launch(c, "rebase_heads"));
         }
-    }
-    if (recv_heads || recv_store) {
         bump_cursors_kernel<<<1, 1, 0, c->stream>>>(c->d_ctr, recv_heads, recv_store);
         GX_TRY(check_launch(c, "bump_cursors"));
     }
+    CUDA_TRY(c, cudaStreamSynchronize(m->comm_stream));  // send buckets are reusable from here on
     CUDA_TRY(c, cudaMemsetAsync(m->counts.p, 0, (size_t)3 * n * sizeof(u64), c->stream));
     m->routed_heads_upto = head_cursor + recv_heads;
     m->routed_store_upto = store_cursor + recv_store;
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (m->use_ipc) {
+        // nobody may reuse (overwrite) its send buckets or inbox before every rank has finished reading: arrival barriers
+        // ordered the copies, this final one orders the end of the upserts that read the inboxes
+        NCCL_TRY(c, ncclAllReduce(m->token.p, m->token.p, 1, ncclFloat, ncclSum, m->comm, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
     return GX_OK;
 }
 

@@ -198,7 +198,8 @@ class GraphBuilder:
     def phase_ms(self) -> dict:
         arr = (C.c_float * 8)()
         self._check(self._lib.gx_phase_ms(self._ctx, C.byref(arr)))
-        return {"parse": arr[0], "insert": arr[1], "exchange": arr[2], "finish": arr[3], "h2d": arr[4]}
+        return {"parse": arr[0], "insert": arr[1], "exchange": arr[2], "finish": arr[3], "h2d": arr[4],
+                "exchange_comm": arr[5], "exchange_insert": arr[6]}
 
     @property
     def kernel_launches(self) -> int:

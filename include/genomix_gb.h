@@ -153,7 +153,8 @@ int gx_mg_exchange(gx_ctx* ctx);
 
 /* ---- timing hooks (device-side, CUDA events on the ctx's stream) ------------------------------ */
 /* Milliseconds spent by the ctx's kernels since gx_reset/gx_create, by phase:
- * [0] line index + parse, [1] extract + insert, [2] exchange, [3] finish (heads + emit), [4] h2d copies. */
+ * [0] line index + parse, [1] extract + insert, [2] exchange (whole), [3] finish (heads + emit), [4] h2d copies,
+ * [5] exchange: NCCL traffic on the communication stream, [6] exchange: upserts of received records. */
 int gx_phase_ms(gx_ctx* ctx, float out_ms[8]);
 /* Number of kernel launches issued by this ctx since creation. */
 uint64_t gx_kernel_launches(gx_ctx* ctx);
