@@ -14,7 +14,7 @@ EXPORTS = [
     "gx_abi_version", "gx_create", "gx_destroy", "gx_reset", "gx_last_error", "gx_get_stats",
     "gx_push_lines", "gx_push_lines_device", "gx_push_fastq", "gx_finish",
     "gx_num_nodes", "gx_record_bytes", "gx_next_records", "gx_records_device", "gx_next_frame",
-    "gx_partition_records", "gx_write_sequence_file", "gx_mg_unique_id", "gx_mg_init", "gx_mg_exchange",
+    "gx_partition_records", "gx_write_sequence_file", "gx_graph_statistics", "gx_mg_unique_id", "gx_mg_init", "gx_mg_exchange",
     "gx_phase_ms", "gx_kernel_launches", "gx_set_stream",
 ]
 
@@ -43,6 +43,23 @@ class GxStats(C.Structure):
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}
+
+
+class GxGraphStats(C.Structure):
+    _fields_ = [
+        ("nodes", C.c_uint64), ("degree_total", C.c_uint64), ("degree_max", C.c_uint64), ("degree_bins", C.c_uint64 * 17),
+        ("coverage_total", C.c_uint64), ("coverage_max", C.c_uint64), ("coverage_bins", C.c_uint64 * 257),
+        ("unflipped_read_ids", C.c_uint64), ("flipped_read_ids", C.c_uint64), ("self_edges", C.c_uint64 * 4),
+        ("path_nodes", C.c_uint64), ("tips_forward", C.c_uint64), ("tips_reverse", C.c_uint64), ("tips_both", C.c_uint64),
+        ("tips_one", C.c_uint64),
+    ]
+
+    def as_dict(self):
+        out = {}
+        for name, typ in self._fields_:
+            v = getattr(self, name)
+            out[name] = int(v) if isinstance(v, int) else [int(x) for x in v]
+        return out
 
 
 _lib = None
@@ -78,6 +95,7 @@ def load() -> C.CDLL:
         "gx_next_frame": (C.c_int, [vp, C.POINTER(u64), u8p, i32, C.POINTER(i32)]),
         "gx_partition_records": (C.c_int, [vp, i32, vp]),
         "gx_write_sequence_file": (C.c_int, [vp, C.c_char_p, u8p, i32, i32, C.POINTER(u64)]),
+        "gx_graph_statistics": (C.c_int, [vp, C.POINTER(GxGraphStats)]),
         "gx_mg_unique_id": (C.c_int, [u8p]),
         "gx_mg_init": (C.c_int, [vp, u8p]),
         "gx_mg_exchange": (C.c_int, [vp]),

@@ -77,6 +77,8 @@ struct gx_ctx {
     DevBuf text, nl_pos, nl_pos2, desc, tile_sums;
     DevBuf hslot, hcount, hstart, hperm, tile_bytes, tile_nodes, records, rec_offsets, parts, dense;
     DevBuf flat_keys, flat_meta, part_keys, part_meta, bucket_count;  // L2-blocked build
+    DevBuf gstats;
+    EmitArgs last_emit{};      // arguments of the last emit (dense node list etc.), reused by gx_graph_statistics
     int blocked_mode = 0;      // 0 auto, 1 never, 2 always (cfg.reserved[2]; tests and A/B runs)
     u32 blocked_buckets = 0;   // 0 auto (cfg.reserved[3])
 
@@ -696,7 +698,7 @@ void gx_destroy(gx_ctx* c) {
     for (auto e : c->event_pool) cudaEventDestroy(e);
     DevBuf* bufs[] = {&c->heads, &c->store, &c->text, &c->nl_pos, &c->nl_pos2, &c->desc, &c->tile_sums, &c->hslot, &c->hcount, &c->hstart,
                       &c->hperm, &c->tile_bytes, &c->tile_nodes, &c->records, &c->rec_offsets, &c->parts, &c->dense,
-                      &c->flat_keys, &c->flat_meta, &c->part_keys, &c->part_meta, &c->bucket_count};
+                      &c->flat_keys, &c->flat_meta, &c->part_keys, &c->part_meta, &c->bucket_count, &c->gstats};
     for (auto* b : bufs) release(*b);
     for (int i = 0; i < 2; ++i) { release(c->spill_keys[i]); release(c->spill_meta[i]); }
     if (c->table) cudaFree(c->table);
@@ -898,6 +900,7 @@ int gx_finish(gx_ctx* c) {
         GX_TRY(check_launch(c, "emit_compact"));
         c->ops->emit_serialise(a, c->stream);
         if (c->n_nodes) GX_TRY(check_launch(c, "emit_serialise"));
+        c->last_emit = a;
     }
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     drain_timers(c);
@@ -1079,6 +1082,22 @@ int gx_write_sequence_file(gx_ctx* c, const char* path, const uint8_t* sync16, i
     if (rc != GX_OK) return rc;
     if (!io_ok) return fail(c, GX_ERR_INVALID, "I/O error while writing %s", path);
     if (bytes_written) *bytes_written = pos;
+    return GX_OK;
+}
+
+int gx_graph_statistics(gx_ctx* c, gx_graph_stats* out) {
+    GX_TRY(require_live(c));
+    if (!c->finished) return fail(c, GX_ERR_STATE, "gx_graph_statistics before gx_finish");
+    if (!out) return fail(c, GX_ERR_INVALID, "null argument");
+    static_assert(sizeof(GraphStatsDev) == sizeof(gx_graph_stats), "device and ABI statistics structs match");
+    cudaSetDevice(c->cfg.device);
+    GX_TRY(ensure(c, c->gstats, sizeof(GraphStatsDev)));
+    CUDA_TRY(c, cudaMemsetAsync(c->gstats.p, 0, sizeof(GraphStatsDev), c->stream));
+    EmitArgs a = c->last_emit;
+    c->ops->graph_stats(a, (GraphStatsDev*)c->gstats.p, c->stream);
+    if (c->n_nodes) GX_TRY(check_launch(c, "graph_stats"));
+    CUDA_TRY(c, cudaMemcpyAsync(out, c->gstats.p, sizeof(GraphStatsDev), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return GX_OK;
 }
 

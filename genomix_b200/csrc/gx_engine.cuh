@@ -859,6 +859,82 @@ __global__ void __launch_bounds__(EM_THREADS) emit_serialise_kernel(EmitArgs a) 
     if (threadIdx.x < tail) g0[head + body * 16u + threadIdx.x] = stage[skew + head + body * 16u + threadIdx.x];
 }
 
+// Fused graph statistics over the dense node list (GraphStatistics.java:78-131; Node.java:820-848).
+struct GraphStatsDev {
+    u64 nodes, degree_total, degree_max, degree_bins[17], coverage_total, coverage_max, coverage_bins[257];
+    u64 unflipped, flipped, self_edges[4], path_nodes, tips_forward, tips_reverse, tips_both, tips_one;
+};
+
+template <int KW>
+__global__ void __launch_bounds__(256) graph_stats_kernel(EmitArgs a, GraphStatsDev* __restrict__ out) {
+    constexpr int DW = KW + 2;
+    __shared__ u32 s_deg[17];
+    __shared__ u32 s_cov[257];
+    for (int i = threadIdx.x; i < 17; i += 256) s_deg[i] = 0;
+    for (int i = threadIdx.x; i < 257; i += 256) s_cov[i] = 0;
+    __syncthreads();
+    u64 deg_tot = 0, cov_tot = 0, unfl = 0, fl = 0, path = 0, tf = 0, tr = 0, tb = 0, to = 0, nodes = 0;
+    u64 deg_max = 0, cov_max = 0, self[4] = {0, 0, 0, 0};
+    for (u64 n = (u64)blockIdx.x * 256 + threadIdx.x; n < a.n_nodes; n += (u64)gridDim.x * 256) {
+        const u64* d = a.dense + n * DW;
+        u64 key[KW];
+#pragma unroll
+        for (int j = 0; j < KW; ++j) key[j] = d[j];
+        const u64 val = d[KW], slot = d[KW + 1];
+        const u32 mask = (u32)(val >> MASK_SHIFT);
+        const u64 cov = val & COUNT_MASK;
+        const u32 out_deg = __popc(mask & 0xffu), in_deg = __popc(mask >> 8);
+        const u32 deg = in_deg + out_deg;
+        ++nodes;
+        deg_tot += deg; deg_max = max(deg_max, (u64)deg);
+        atomicAdd(&s_deg[deg], 1u);
+        cov_tot += cov; cov_max = max(cov_max, cov);
+        atomicAdd(&s_cov[cov > 256 ? 256 : (u32)cov], 1u);
+        if (in_deg == 1 && out_deg == 1) ++path;
+        if (out_deg == 0) ++tf;
+        if (in_deg == 0) ++tr;
+        if (in_deg == 0 && out_deg == 0) ++tb;
+        if ((in_deg == 0) != (out_deg == 0)) ++to;
+        u64 rcx[KW];
+        revcomp_key<KW>(key, a.k, rcx);
+        for (u32 rest = mask; rest; rest &= rest - 1u) {
+            const u32 bit = (u32)__ffs(rest) - 1u, t = bit >> 2, b = bit & 3u;
+            u64 nk[KW];
+            if (t == 0) key_append<KW>(key, a.k, b, nk);
+            else if (t == 1) key_prepend<KW>(rcx, a.k, 3u - b, nk);
+            else if (t == 2) key_append<KW>(rcx, a.k, 3u - b, nk);
+            else key_prepend<KW>(key, a.k, b, nk);
+            if (key_eq<KW>(nk, key)) ++self[t];
+        }
+        if (a.hcount) {
+            const u32 nh = a.hcount[slot];
+            if (nh) {
+                const Head<KW>* heads = reinterpret_cast<const Head<KW>*>(a.heads);
+                const u32* v = a.hperm + a.hstart[slot];
+                for (u32 i = 0; i < nh; ++i) { if (heads[v[i]].flipped) ++fl; else ++unfl; }
+            }
+        }
+    }
+    // block reductions, then one atomic per counter and CTA
+    const u64 r_nodes = block_reduce_sum<256>(nodes), r_deg = block_reduce_sum<256>(deg_tot), r_cov = block_reduce_sum<256>(cov_tot);
+    const u64 r_unfl = block_reduce_sum<256>(unfl), r_fl = block_reduce_sum<256>(fl), r_path = block_reduce_sum<256>(path);
+    const u64 r_tf = block_reduce_sum<256>(tf), r_tr = block_reduce_sum<256>(tr), r_tb = block_reduce_sum<256>(tb), r_to = block_reduce_sum<256>(to);
+    u64 r_self[4];
+    for (int t = 0; t < 4; ++t) r_self[t] = block_reduce_sum<256>(self[t]);
+    atomicMax(&out->degree_max, deg_max);
+    atomicMax(&out->coverage_max, cov_max);
+    if (threadIdx.x == 0) {
+        atomicAdd(&out->nodes, r_nodes); atomicAdd(&out->degree_total, r_deg); atomicAdd(&out->coverage_total, r_cov);
+        atomicAdd(&out->unflipped, r_unfl); atomicAdd(&out->flipped, r_fl); atomicAdd(&out->path_nodes, r_path);
+        atomicAdd(&out->tips_forward, r_tf); atomicAdd(&out->tips_reverse, r_tr); atomicAdd(&out->tips_both, r_tb);
+        atomicAdd(&out->tips_one, r_to);
+        for (int t = 0; t < 4; ++t) atomicAdd(&out->self_edges[t], r_self[t]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 17; i += 256) if (s_deg[i]) atomicAdd(&out->degree_bins[i], (u64)s_deg[i]);
+    for (int i = threadIdx.x; i < 257; i += 256) if (s_cov[i]) atomicAdd(&out->coverage_bins[i], (u64)s_cov[i]);
+}
+
 // R3: KmerPartitionComputerFactory.partition over emitted records (KmerPartitionComputerFactory.java:28-52):
 // h = 1; h = 31*h + (signed byte) over the Kmer field bytes; h < 0 -> -(h+1); h % nParts
 static __global__ void __launch_bounds__(256) partition_records_kernel(const uint8_t* __restrict__ records,
@@ -896,6 +972,7 @@ struct EngineOps {
     void (*emit_size)(const EmitArgs& a, cudaStream_t st);
     void (*emit_compact)(const EmitArgs& a, cudaStream_t st);
     void (*emit_serialise)(const EmitArgs& a, cudaStream_t st);
+    void (*graph_stats)(const EmitArgs& a, GraphStatsDev* out, cudaStream_t st);
     void (*route_heads)(const HeadRouteArgs& a, cudaStream_t st);
     void (*rebase_heads)(void* heads, u64 first, u64 n, u64 store_base, cudaStream_t st);
     int (*prepare)();  // one-time function attributes (dynamic shared memory opt-in)

@@ -55,6 +55,10 @@ void l_emit_serialise(const EmitArgs& a, cudaStream_t st) {
     if (a.n_nodes == 0) return;
     emit_serialise_kernel<KW><<<(unsigned)((a.n_nodes + EM_THREADS - 1) / EM_THREADS), EM_THREADS, a.stage_bytes, st>>>(a);
 }
+void l_graph_stats(const EmitArgs& a, GraphStatsDev* out, cudaStream_t st) {
+    if (a.n_nodes == 0) return;
+    graph_stats_kernel<KW><<<grid_for(a.n_nodes, 256, 148 * 8), 256, 0, st>>>(a, out);
+}
 void l_route_heads(const HeadRouteArgs& a, cudaStream_t st) {
     if (a.n == 0) return;
     route_heads_kernel<KW><<<(unsigned)((a.n + 255) / 256), 256, 0, st>>>(a);
@@ -82,6 +86,7 @@ const EngineOps OPS = {KW,
                        l_emit_size,
                        l_emit_compact,
                        l_emit_serialise,
+                       l_graph_stats,
                        l_route_heads,
                        l_rebase_heads,
                        l_prepare};

@@ -195,6 +195,12 @@ class GraphBuilder:
         self._check(self._lib.gx_get_stats(self._ctx, C.byref(s)))
         return s.as_dict()
 
+    def graph_statistics(self) -> dict:
+        """Node counters of the reference's GraphStatistics job, reduced on the GPU (after finish())."""
+        g = _lib.GxGraphStats()
+        self._check(self._lib.gx_graph_statistics(self._ctx, C.byref(g)))
+        return g.as_dict()
+
     def phase_ms(self) -> dict:
         arr = (C.c_float * 8)()
         self._check(self._lib.gx_phase_ms(self._ctx, C.byref(arr)))

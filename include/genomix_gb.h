@@ -142,6 +142,23 @@ int gx_write_sequence_file(gx_ctx* ctx, const char* path, const uint8_t* sync16,
  * abs, % n_parts): writes one int32 per node into host_parts (n_nodes entries). */
 int gx_partition_records(gx_ctx* ctx, int32_t n_parts, int32_t* host_parts);
 
+/* ---- graph statistics --------------------------------------------------------
+ * The per-node counters of the reference's post-build statistics job (genomix/genomix-hadoop/src/main/java/edu/uci/ics/genomix/
+ * hadoop/utils/GraphStatistics.java:78-131) as one fused reduction over this rank's nodes, without leaving the GPU:
+ * inDegree = |RF|+|RR|, outDegree = |FF|+|FR| (Node.java:820-848). */
+typedef struct gx_graph_stats {
+    uint64_t nodes;
+    uint64_t degree_total, degree_max;
+    uint64_t degree_bins[17];        /* inDegree + outDegree, 0..16 */
+    uint64_t coverage_total, coverage_max;
+    uint64_t coverage_bins[257];     /* Math.round(coverage) 0..255, last bin = 256 and above */
+    uint64_t unflipped_read_ids, flipped_read_ids;
+    uint64_t self_edges[4];          /* totals/selfEdge-FF,FR,RF,RR */
+    uint64_t path_nodes;             /* inDegree == 1 && outDegree == 1 */
+    uint64_t tips_forward, tips_reverse, tips_both, tips_one;
+} gx_graph_stats;
+int gx_graph_statistics(gx_ctx* ctx, gx_graph_stats* out);   /* after gx_finish */
+
 /* ---- multi-GPU (n_ranks > 1): hash-partitioned exchange ----------------------------------------
  * One process per GPU. Bootstrap: rank 0 calls gx_mg_unique_id, the host side broadcasts the 128
  * bytes (torch.distributed / MPI / Hyracks RPC), every rank calls gx_mg_init. After the last

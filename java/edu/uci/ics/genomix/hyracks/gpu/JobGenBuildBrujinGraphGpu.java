@@ -1,0 +1,56 @@
+package edu.uci.ics.genomix.hyracks.gpu;
+
+import java.io.IOException;
+import java.util.Map;
+
+import edu.uci.ics.genomix.data.config.GenomixJobConf;
+import edu.uci.ics.genomix.hyracks.graph.dataflow.KmerNodePairSequenceWriterFactory;
+import edu.uci.ics.genomix.hyracks.graph.dataflow.ReadsKeyValueParserFactory;
+import edu.uci.ics.genomix.hyracks.graph.job.JobGenBuildBrujinGraph;
+import edu.uci.ics.hyracks.api.constraints.PartitionConstraintHelper;
+import edu.uci.ics.hyracks.api.exceptions.HyracksDataException;
+import edu.uci.ics.hyracks.api.exceptions.HyracksException;
+import edu.uci.ics.hyracks.api.job.JobSpecification;
+import edu.uci.ics.hyracks.dataflow.std.connectors.OneToOneConnectorDescriptor;
+import edu.uci.ics.hyracks.hdfs.dataflow.HDFSReadOperatorDescriptor;
+import edu.uci.ics.hyracks.hdfs.dataflow.HDFSWriteOperatorDescriptor;
+import edu.uci.ics.hyracks.hdfs.scheduler.Scheduler;
+
+/**
+ * The fast plan for genomix.conf.hyracksGroupby=GPU: HDFS read (GPU parser) -> HDFS write (the unchanged
+ * KmerNodePairSequenceWriterFactory). It replaces the six-operator plan of JobGenBuildBrujinGraph.assignJob
+ * (genomix-hyracks/src/main/java/edu/uci/ics/genomix/hyracks/graph/job/JobGenBuildBrujinGraph.java:79-143): the external
+ * sort, both pre-clustered group-bys and the M:N hash-partitioning merging connector run inside libgenomix_gb.
+ */
+public class JobGenBuildBrujinGraphGpu extends JobGenBuildBrujinGraph {
+    private static final long serialVersionUID = 1L;
+    private final int gpusPerNode;
+
+    public JobGenBuildBrujinGraphGpu(GenomixJobConf job, Scheduler scheduler, final Map<String, Integer> ncMap,
+            int numPartitionPerMachine, int gpusPerNode) throws HyracksDataException {
+        super(job, scheduler, ncMap, numPartitionPerMachine);
+        this.gpusPerNode = gpusPerNode;
+    }
+
+    @Override
+    public JobSpecification assignJob(JobSpecification jobSpec) throws HyracksException {
+        try {
+            int nPartitions = readSchedule.length;
+            byte[] ncclId = nPartitions > 1 ? GenomixGb.mgUniqueId() : null;
+            HDFSReadOperatorDescriptor read = new HDFSReadOperatorDescriptor(jobSpec,
+                    ReadsKeyValueParserFactory.readKmerOutputRec, hadoopJobConfFactory.getConf(), splits, readSchedule,
+                    new GpuReadsKeyValueParserFactory(hadoopJobConfFactory.getConf(), gpusPerNode, nPartitions, ncclId));
+            PartitionConstraintHelper.addAbsoluteLocationConstraint(jobSpec, read, ncNodeNames);
+
+            HDFSWriteOperatorDescriptor write = new HDFSWriteOperatorDescriptor(jobSpec, hadoopJobConfFactory.getConf(),
+                    new KmerNodePairSequenceWriterFactory(hadoopJobConfFactory.getConf()));
+            PartitionConstraintHelper.addAbsoluteLocationConstraint(jobSpec, write, ncNodeNames);
+
+            jobSpec.connect(new OneToOneConnectorDescriptor(jobSpec), read, 0, write, 0);
+            jobSpec.addRoot(write);
+            return jobSpec;
+        } catch (IOException e) {
+            throw new HyracksException(e);
+        }
+    }
+}

@@ -253,3 +253,42 @@ def test_cfg1_full_size():
             n, _ = gx.types.Node.read(val, 0)
             tot += int(n.coverage)
         assert tot == st["kmer_occurrences"]
+
+
+def test_graph_statistics_match_reference_definitions():
+    """gx_graph_statistics against GraphStatistics.java:78-131 evaluated on the decoded records"""
+    gx = _gx()
+    rng = np.random.default_rng(31)
+    text = random_reads_text(rng, 500, 40, 70, paired=True, genome_len=1500) + b"9000\t" + b"AC" * 30 + b"\n9004\t" + b"A" * 40 + b"\n"
+    for k in (4, 21, 33):
+        with gx.GraphBuilder(k) as gb:
+            gb.push_lines(text)
+            gb.finish()
+            got = gb.graph_statistics()
+            recs = list(gx.types.iter_records(gb.records()))
+        want = {"nodes": 0, "degree_total": 0, "degree_max": 0, "degree_bins": [0] * 17, "coverage_total": 0, "coverage_max": 0,
+                "coverage_bins": [0] * 257, "unflipped_read_ids": 0, "flipped_read_ids": 0, "self_edges": [0] * 4, "path_nodes": 0,
+                "tips_forward": 0, "tips_reverse": 0, "tips_both": 0, "tips_one": 0}
+        for key, val in recs:
+            node, _ = gx.types.Node.read(val, 0)
+            sizes = [len(e) if e else 0 for e in node.edges]
+            out_deg, in_deg = sizes[0] + sizes[1], sizes[2] + sizes[3]   # DIR.FORWARD = {FF, FR}, DIR.REVERSE = {RF, RR}
+            want["nodes"] += 1
+            want["degree_total"] += in_deg + out_deg
+            want["degree_max"] = max(want["degree_max"], in_deg + out_deg)
+            want["degree_bins"][in_deg + out_deg] += 1
+            cov = int(round(node.coverage))
+            want["coverage_total"] += cov
+            want["coverage_max"] = max(want["coverage_max"], cov)
+            want["coverage_bins"][min(cov, 256)] += 1
+            want["unflipped_read_ids"] += len(node.unflipped or [])
+            want["flipped_read_ids"] += len(node.flipped or [])
+            for et in range(4):
+                want["self_edges"][et] += sum(1 for e in (node.edges[et] or []) if e.write() == key)
+            want["path_nodes"] += in_deg == 1 and out_deg == 1
+            want["tips_forward"] += out_deg == 0
+            want["tips_reverse"] += in_deg == 0
+            want["tips_both"] += in_deg == 0 and out_deg == 0
+            want["tips_one"] += (in_deg == 0) != (out_deg == 0)
+        assert got == want, k
+        assert want["self_edges"] != [0, 0, 0, 0]
