@@ -7,6 +7,7 @@ import edu.uci.ics.genomix.data.config.GenomixJobConf;
 import edu.uci.ics.genomix.hyracks.graph.dataflow.KmerNodePairSequenceWriterFactory;
 import edu.uci.ics.genomix.hyracks.graph.dataflow.ReadsKeyValueParserFactory;
 import edu.uci.ics.genomix.hyracks.graph.job.JobGenBuildBrujinGraph;
+import edu.uci.ics.hyracks.api.client.NodeControllerInfo;
 import edu.uci.ics.hyracks.api.constraints.PartitionConstraintHelper;
 import edu.uci.ics.hyracks.api.exceptions.HyracksDataException;
 import edu.uci.ics.hyracks.api.exceptions.HyracksException;
@@ -26,19 +27,19 @@ public class JobGenBuildBrujinGraphGpu extends JobGenBuildBrujinGraph {
     private static final long serialVersionUID = 1L;
     private final int gpusPerNode;
 
-    public JobGenBuildBrujinGraphGpu(GenomixJobConf job, Scheduler scheduler, final Map<String, Integer> ncMap,
+    public JobGenBuildBrujinGraphGpu(GenomixJobConf job, Scheduler scheduler, final Map<String, NodeControllerInfo> ncMap,
             int numPartitionPerMachine, int gpusPerNode) throws HyracksDataException {
         super(job, scheduler, ncMap, numPartitionPerMachine);
         this.gpusPerNode = gpusPerNode;
     }
 
     @Override
-    public JobSpecification assignJob(JobSpecification jobSpec) throws HyracksException {
+    protected JobSpecification assignJob(JobSpecification jobSpec) throws HyracksException {
         try {
             int nPartitions = readSchedule.length;
             byte[] ncclId = nPartitions > 1 ? GenomixGb.mgUniqueId() : null;
             HDFSReadOperatorDescriptor read = new HDFSReadOperatorDescriptor(jobSpec,
-                    ReadsKeyValueParserFactory.readKmerOutputRec, hadoopJobConfFactory.getConf(), splits, readSchedule,
+                    ReadsKeyValueParserFactory.readKmerOutputRec, hadoopJobConfFactory.getConf(), getInputSplit(), readSchedule,
                     new GpuReadsKeyValueParserFactory(hadoopJobConfFactory.getConf(), gpusPerNode, nPartitions, ncclId));
             PartitionConstraintHelper.addAbsoluteLocationConstraint(jobSpec, read, ncNodeNames);
 
