@@ -278,7 +278,8 @@ def main():
             traffic = None
     n_insert_launches = max(1, -(-dev_text.numel() // (64 << 20)))
     roof = {
-        "bound": "hbm", "kernel": "extract_kernel<KW,false> (k-mer extract + hash upsert)",
+        "bound": "hbm", "kernel": "extract_kernel<KW,EX_UPSERT> (k-mer extract + hash upsert)" if world == 1 else
+        "extract_kernel<KW,EX_ROUTE> (k-mer extract + own-key upsert + routing); received keys: insert_records_kernel",
         "achieved": insert_bytes / (insert_ms * 1e-3) / 1e9 if insert_ms > 0 else None,
         "peak": peak, "unit": "GB/s", "peak_source": peak_src,
         "frac": (insert_bytes / (insert_ms * 1e-3) / 1e9 / peak) if insert_ms > 0 else None,
