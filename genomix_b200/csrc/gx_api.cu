@@ -93,6 +93,8 @@ struct gx_ctx {
     u64 frame_byte_cursor = 0, frame_rec_cursor = 0;
 
     void* mg = nullptr;  // MgState (gx_mg.inl) when n_ranks > 1
+    cudaStream_t aux_stream = nullptr;   // L2 prefetch of the next table region (blocked build)
+    cudaEvent_t aux_event = nullptr;
 
     // spill area (two buffers, swapped while one is being re-inserted) and the new-key predictor
     DevBuf spill_keys[2], spill_meta[2];
@@ -287,6 +289,7 @@ int reserve_room(gx_ctx* c, u64 distinct, u64 min_room, u64 hint, u64* room) {
         c->ops->rehash(c->table, c->capacity, nt, ncap, c->stream);
         GX_TRY(check_launch(c, "rehash"));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        if (c->aux_stream) CUDA_TRY(c, cudaStreamSynchronize(c->aux_stream));  // a region prefetch may still read the old table
         CUDA_TRY(c, cudaFree(c->table));
         ++c->grows;
         c->table = nt;
@@ -329,6 +332,7 @@ int grow_table(gx_ctx* c) {
     c->ops->rehash(c->table, c->capacity, nt, ncap, c->stream);
     GX_TRY(check_launch(c, "rehash"));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->aux_stream) CUDA_TRY(c, cudaStreamSynchronize(c->aux_stream));
     CUDA_TRY(c, cudaFree(c->table));
     ++c->grows;
     c->table = nt;
@@ -376,6 +380,16 @@ int blocked_insert(gx_ctx* c, const u64* keys, const unsigned short* meta, const
             ScopedPhase ph(c, PH_INSERT);
             for (u32 i = b; i < e; ++i) {
                 const u64 cnt = offsets[i + 1] - offsets[i];
+                // while region i is upserted, region i+1 is prefetched into L2 on the auxiliary stream
+                if (c->aux_stream && i + 1 < n_buckets) {
+                    const u64 lo = (u64)(((unsigned __int128)(i + 1) * c->capacity) / n_buckets);
+                    const u64 hi = (u64)(((unsigned __int128)(i + 2) * c->capacity) / n_buckets);
+                    cudaEventRecord(c->aux_event, c->stream);
+                    cudaStreamWaitEvent(c->aux_stream, c->aux_event, 0);
+                    prefetch_region_kernel<<<148, 256, 0, c->aux_stream>>>((const uint8_t*)c->table + lo * c->ops->slot_bytes,
+                                                                           (hi - lo) * c->ops->slot_bytes);
+                    ++c->launches;
+                }
                 if (!cnt) continue;
                 c->ops->insert_records(keys + offsets[i] * c->kw, meta + offsets[i], nullptr, cnt, c->table, c->capacity, c->d_ctr,
                                        c->stream);
@@ -400,11 +414,11 @@ int blocked_chunk(gx_ctx* c, const uint8_t* d_text, size_t n, u64 n_lines, u64 c
     GX_TRY(ensure(c, c->flat_meta, (size_t)chunk_occ * sizeof(unsigned short)));
     GX_TRY(ensure(c, c->part_keys, (size_t)chunk_occ * c->kw * sizeof(u64)));
     GX_TRY(ensure(c, c->part_meta, (size_t)chunk_occ * sizeof(unsigned short)));
-    GX_TRY(ensure(c, c->bucket_count, (size_t)MAX_BUCKETS * sizeof(u64)));
+    GX_TRY(ensure(c, c->bucket_count, (size_t)MAX_BUCKETS * BUCKET_PAD * sizeof(u64)));
     std::vector<u64> counts(n_buckets), offsets(n_buckets + 1, 0);
     {
         ScopedPhase ph(c, PH_INSERT);
-        CUDA_TRY(c, cudaMemsetAsync(c->bucket_count.p, 0, (size_t)n_buckets * sizeof(u64), c->stream));
+        CUDA_TRY(c, cudaMemsetAsync(c->bucket_count.p, 0, (size_t)n_buckets * BUCKET_PAD * sizeof(u64), c->stream));
         ExtractArgs a{};
         a.text = d_text; a.n_text = n;
         a.desc = (const LineDesc*)c->desc.p; a.n_lines = n_lines;
@@ -418,7 +432,8 @@ int blocked_chunk(gx_ctx* c, const uint8_t* d_text, size_t n, u64 n_lines, u64 c
         a.bucket_count = (u64*)c->bucket_count.p; a.n_buckets = n_buckets;
         c->ops->extract_flat(a, c->stream);
         GX_TRY(check_launch(c, "extract_flat"));
-        CUDA_TRY(c, cudaMemcpyAsync(counts.data(), c->bucket_count.p, (size_t)n_buckets * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaMemcpy2DAsync(counts.data(), sizeof(u64), c->bucket_count.p, BUCKET_PAD * sizeof(u64), sizeof(u64), n_buckets,
+                                      cudaMemcpyDeviceToHost, c->stream));
     }
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     drain_timers(c);
@@ -428,7 +443,8 @@ int blocked_chunk(gx_ctx* c, const uint8_t* d_text, size_t n, u64 n_lines, u64 c
                                 (unsigned long long)offsets[n_buckets], (unsigned long long)chunk_occ);
     {
         ScopedPhase ph(c, PH_INSERT);
-        CUDA_TRY(c, cudaMemcpyAsync(c->bucket_count.p, offsets.data(), (size_t)n_buckets * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaMemcpy2DAsync(c->bucket_count.p, BUCKET_PAD * sizeof(u64), offsets.data(), sizeof(u64), sizeof(u64), n_buckets,
+                                      cudaMemcpyHostToDevice, c->stream));
         c->ops->partition_flat((const u64*)c->flat_keys.p, (const unsigned short*)c->flat_meta.p, chunk_occ, n_buckets,
                                (u64*)c->bucket_count.p, (u64*)c->part_keys.p, (unsigned short*)c->part_meta.p, c->stream);
         GX_TRY(check_launch(c, "partition_flat"));
@@ -644,6 +660,8 @@ int gx_create(const gx_config* cfg, gx_ctx** out) {
     auto bail = [&](int code) { g_create_error = c->err; gx_destroy(c); return code; };
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(c, GX_ERR_CUDA, "stream"));
     c->own_stream = true;
+    cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&c->aux_event, cudaEventDisableTiming);
     if (cudaMalloc((void**)&c->d_ctr, sizeof(Counters)) != cudaSuccess) return bail(fail(c, GX_ERR_NOMEM, "counters"));
     if (cudaMallocHost((void**)&c->h_ctr, sizeof(Counters)) != cudaSuccess) return bail(fail(c, GX_ERR_NOMEM, "pinned counters"));
     if (c->ops->prepare() != 0) return bail(fail(c, GX_ERR_CUDA, "cudaFuncSetAttribute failed"));
@@ -704,6 +722,8 @@ void gx_destroy(gx_ctx* c) {
     if (c->table) cudaFree(c->table);
     if (c->d_ctr) cudaFree(c->d_ctr);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
+    if (c->aux_stream) { cudaStreamSynchronize(c->aux_stream); cudaStreamDestroy(c->aux_stream); }
+    if (c->aux_event) cudaEventDestroy(c->aux_event);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

@@ -27,6 +27,7 @@ static constexpr int WIN_POSITIONS = 4 * WIN_BYTES - 160;   // k-mer start posit
 #endif
 static constexpr int EX_BATCH = GX_EX_BATCH;                // groups of 30 positions in flight per warp
 static constexpr int MAX_BUCKETS = 1024;                    // table regions of the L2-blocked build
+static constexpr int BUCKET_PAD = 16;                       // per-region counters live 128 B apart (one L2 line each)
 
 // Region (bucket) of a key: regions are contiguous slot ranges because slot_of() is monotone in the hash too.
 __host__ __device__ __forceinline__ u32 bucket_of(u64 h, u32 n_buckets) {
@@ -324,7 +325,7 @@ __global__ void __launch_bounds__(EX_THREADS, GX_EX_MIN_BLOCKS) extract_kernel(E
     if constexpr (FLAT) {
         __syncthreads();
         for (u32 i = threadIdx.x; i < a.n_buckets; i += EX_THREADS)
-            if (bucket_hist[i]) atomicAdd(a.bucket_count + i, (u64)bucket_hist[i]);
+            if (bucket_hist[i]) atomicAdd(a.bucket_count + (size_t)i * BUCKET_PAD, (u64)bucket_hist[i]);
     }
 }
 
@@ -349,10 +350,17 @@ __global__ void __launch_bounds__(256) insert_records_kernel(const u64* __restri
     if ((threadIdx.x & 31) == 0 && new_slots) atomicAdd(&ctr->distinct, (u64)new_slots);
 }
 
+// L2-blocked build: pull the next table region into L2 with sequential line prefetches while the current region is being
+// upserted, so that the random first touches of a region are L2 hits too.
+static __global__ void __launch_bounds__(256) prefetch_region_kernel(const uint8_t* __restrict__ base, u64 bytes) {
+    for (u64 off = ((u64)blockIdx.x * 256 + threadIdx.x) * 128; off < bytes; off += (u64)gridDim.x * 256 * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+}
+
 // L2-blocked build, pass 2: scatter the flat (key, mask) records into per-region segments whose exact
 // offsets come from the histogram taken in pass 1 (bucket_cursor starts at the segment offsets).
 static constexpr int PT_THREADS = 256;
-static constexpr int PT_ITEMS = 8;
+static constexpr int PT_ITEMS = 16;
 template <int KW>
 __global__ void __launch_bounds__(PT_THREADS) partition_flat_kernel(const u64* __restrict__ flat_keys,
                                                                     const unsigned short* __restrict__ flat_meta, u64 n,
@@ -379,7 +387,7 @@ __global__ void __launch_bounds__(PT_THREADS) partition_flat_kernel(const u64* _
     }
     __syncthreads();
     for (u32 i = threadIdx.x; i < n_buckets; i += PT_THREADS)
-        base[i] = hist[i] ? atomicAdd(bucket_cursor + i, (u64)hist[i]) : 0ull;
+        base[i] = hist[i] ? atomicAdd(bucket_cursor + (size_t)i * BUCKET_PAD, (u64)hist[i]) : 0ull;
     __syncthreads();
 #pragma unroll
     for (int it = 0; it < PT_ITEMS; ++it) {

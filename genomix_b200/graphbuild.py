@@ -37,10 +37,10 @@ class GraphBuilder:
         cfg.rank = rank
         cfg.n_ranks = n_ranks
         cfg.expected_kmers = expected_kmers
-        cfg.reserved[0] = chunk_bytes
+        cfg.reserved[0] = chunk_bytes or int(os.environ.get("GENOMIX_GB_CHUNK", "0"))
         cfg.reserved[1] = l2_fetch_granularity or int(os.environ.get("GENOMIX_GB_L2_GRAN", "0"))
         cfg.reserved[2] = blocked_mode or int(os.environ.get("GENOMIX_GB_BLOCKED", "0"))   # 0 auto, 1 never, 2 always
-        cfg.reserved[3] = blocked_buckets
+        cfg.reserved[3] = blocked_buckets or int(os.environ.get("GENOMIX_GB_BUCKETS", "0"))
         self.kmer_length = kmer_length
         self._ctx = C.c_void_p()
         st = self._lib.gx_create(C.byref(cfg), C.byref(self._ctx))
