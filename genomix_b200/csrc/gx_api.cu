@@ -630,6 +630,8 @@ int gx_create(const gx_config* cfg, gx_ctx** out) {
         return fail(nullptr, GX_ERR_INVALID, "gx_create: abi_version %d != %d", cfg->abi_version, GX_ABI_VERSION);
     if (cfg->kmer_length < 1 || cfg->kmer_length > 32 * GX_MAX_KW)
         return fail(nullptr, GX_ERR_INVALID, "gx_create: kmer_length %d outside [1, %d]", cfg->kmer_length, 32 * GX_MAX_KW);
+    if (cfg->sort_output != 0)
+        return fail(nullptr, GX_ERR_INVALID, "gx_create: sort_output is not implemented (record order is not observable downstream)");
     if (cfg->n_ranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->n_ranks)
         return fail(nullptr, GX_ERR_INVALID, "gx_create: bad rank %d of %d", cfg->rank, cfg->n_ranks);
     int n_dev = 0;

@@ -1,9 +1,11 @@
 // gx_engine.cuh -- the KW-templated kernels of the graph-build path and their launchers.
 //
-//   K1+K2  extract_insert_kernel   read -> canonical k-mers -> hash-table upsert   (single GPU: fused)
-//   K1x    extract_route_kernel    read -> k-mer records bucketed by owner GPU     (multi GPU)
-//   K2x    insert_records_kernel   received records -> upsert
-//   K3     heads_* + emit_*        read-head grouping, sizing, Node serialisation
+//   K1+K2  extract_kernel<KW,EX_UPSERT>  read -> canonical k-mers -> hash-table upsert          (single GPU: fused)
+//   K1x    extract_kernel<KW,EX_ROUTE>   same, own keys upserted, the rest bucketed by owner GPU (multi GPU)
+//          extract_kernel<KW,EX_FLAT> + partition_flat_kernel                                   (opt-in L2-blocked build)
+//   K2x    insert_records_kernel         (key, mask) records -> upsert (received from peers / table regions / spills)
+//   K3     heads_* + emit_size/compact/serialise  read-head grouping, sizing, dense node list, Node serialisation
+//          graph_stats_kernel, partition_records_kernel, route/rebase_heads
 //
 // Reference semantics restated by each kernel are cited at the kernel.
 #pragma once

@@ -60,9 +60,13 @@ typedef struct gx_config {
     int32_t device;             /* CUDA device ordinal */
     int32_t rank;               /* this process's partition index, 0 <= rank < n_ranks */
     int32_t n_ranks;            /* number of GPUs sharing the key space (1 = single GPU) */
-    int32_t sort_output;        /* !=0: records leave in KmerPointable order (KmerPointable.java:94-107); 0: table order */
+    int32_t sort_output;        /* must be 0: records leave in table-slot order. (The reference writes each part file in
+                                 * KmerPointable order, KmerPointable.java:94-107, but the Pregelix loader re-sorts, so the order
+                                 * is not observable downstream; a sorted stream is not implemented -> GX_ERR_INVALID.) */
     uint64_t expected_kmers;    /* hint: distinct canonical k-mers this rank will own (0 = grow on demand) */
-    uint64_t reserved[4];
+    uint64_t reserved[4];       /* tuning/test knobs, 0 = default: [0] internal chunk bytes, [1] L2 fetch granularity,
+                                 * [2] low byte: build mode (0/1 direct, 2 L2-blocked), bit 8: test hook (predictor claims no new
+                                 * keys), [3] number of table regions of the blocked build */
 } gx_config;
 
 /* Counters of the job so far (the reference only logs wall time: GenomixDriver.java:459,467). */
