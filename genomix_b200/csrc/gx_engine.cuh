@@ -29,6 +29,7 @@ static constexpr int WIN_POSITIONS = 4 * WIN_BYTES - 160;   // k-mer start posit
 #endif
 static constexpr int EX_BATCH = GX_EX_BATCH;                // groups of 30 positions in flight per warp
 static constexpr int MAX_BUCKETS = 1024;                    // table regions of the L2-blocked build
+static constexpr int ROUTE_MAXG = 32;                       // ranks handled by the parallel-reservation routing path
 static constexpr int BUCKET_PAD = 16;                       // per-region counters live 128 B apart (one L2 line each)
 
 // Region (bucket) of a key: regions are contiguous slot ranges because slot_of() is monotone in the hash too.
@@ -163,6 +164,8 @@ __global__ void __launch_bounds__(EX_THREADS, GX_EX_MIN_BLOCKS) extract_kernel(E
     __shared__ u64 stash_k[STASH ? EX_WARPS : 1][NB][KW][32];
     __shared__ unsigned short stash_m[STASH ? EX_WARPS : 1][NB][32];
     __shared__ unsigned short stash_o[(STASH && ROUTE) ? EX_WARPS : 1][NB][32];
+    __shared__ unsigned short route_cnt[ROUTE ? EX_WARPS : 1][ROUTE ? NB * ROUTE_MAXG : 1];  // records per (row, destination)
+    __shared__ u64 route_base[ROUTE ? EX_WARPS : 1][ROUTE ? ROUTE_MAXG : 1];               // reserved start per destination
     __shared__ u32 bucket_hist[FLAT ? MAX_BUCKETS : 1];  // this CTA's records per table region (EX_FLAT)
     if constexpr (FLAT) {
         for (u32 i = threadIdx.x; i < a.n_buckets; i += EX_THREADS) bucket_hist[i] = 0;
@@ -286,33 +289,75 @@ __global__ void __launch_bounds__(EX_THREADS, GX_EX_MIN_BLOCKS) extract_kernel(E
                         }
                     }
                     if constexpr (ROUTE) {
-                        // append the batch to the owners' send buckets: per destination one reservation for the whole
-                        // warp (ballot counts), then every lane writes its records at base + rank
+                        // Append the batch to the owners' send buckets. One reservation per (warp, destination) covers the
+                        // whole batch, and the reservations of ALL destinations are issued together (lane d reserves for
+                        // destination d), so the warp waits for one atomic round trip per batch, not one per destination.
                         if (__any_sync(0xffffffffu, acts != 0)) {
-                            for (u32 dest = 0; dest < a.n_ranks; ++dest) {
-                                if (dest == a.rank) continue;
-                                u32 mine[NB];
-                                u32 total = 0;
+                            if (a.n_ranks <= ROUTE_MAXG) {
+                                unsigned short* C = route_cnt[warp];
+                                for (u32 i = lane; i < NB * ROUTE_MAXG; i += 32) C[i] = 0;
+                                __syncwarp();
+                                u32 rank_in_row[NB];
 #pragma unroll
                                 for (int j = 0; j < NB; ++j) {
-                                    mine[j] = __ballot_sync(0xffffffffu, ((acts >> j) & 1u) && stash_o[warp][j][lane] == dest);
-                                    total += __popc(mine[j]);
-                                }
-                                if (total == 0) continue;
-                                u64 base = 0;
-                                if (lane == 0) base = atomicAdd(a.route_count + dest, (u64)total);
-                                base = __shfl_sync(0xffffffffu, base, 0);
-                                u64* kbase = a.route_keys[dest];
-                                unsigned short* mbase = a.route_meta[dest];
-#pragma unroll
-                                for (int j = 0; j < NB; ++j) {
-                                    if ((mine[j] >> lane) & 1u) {
-                                        const u64 idx = base + __popc(mine[j] & lane_lt);
-#pragma unroll
-                                        for (int i = 0; i < KW; ++i) kbase[idx * KW + i] = stash_k[warp][j][i][lane];
-                                        mbase[idx] = stash_m[warp][j][lane];
+                                    const bool has = (acts >> j) & 1u;
+                                    const u32 rowmask = __ballot_sync(0xffffffffu, has);
+                                    rank_in_row[j] = 0;
+                                    if (has) {
+                                        const u32 dst = stash_o[warp][j][lane];
+                                        const u32 peers = __match_any_sync(rowmask, dst);
+                                        rank_in_row[j] = __popc(peers & lane_lt);
+                                        if (lane == __ffs(peers) - 1) C[j * ROUTE_MAXG + dst] = (unsigned short)__popc(peers);
                                     }
-                                    base += __popc(mine[j]);
+                                }
+                                __syncwarp();
+                                for (u32 dst = lane; dst < a.n_ranks; dst += 32) {
+                                    u32 tot = 0;
+#pragma unroll
+                                    for (int j = 0; j < NB; ++j) tot += C[j * ROUTE_MAXG + dst];
+                                    route_base[warp][dst] = tot ? atomicAdd(a.route_count + dst, (u64)tot) : 0ull;
+                                }
+                                __syncwarp();
+#pragma unroll
+                                for (int j = 0; j < NB; ++j) {
+                                    if (!((acts >> j) & 1u)) continue;
+                                    const u32 dst = stash_o[warp][j][lane];
+                                    u64 idx = route_base[warp][dst] + rank_in_row[j];
+#pragma unroll
+                                    for (int jj = 0; jj < NB; ++jj)
+                                        if (jj < j) idx += C[jj * ROUTE_MAXG + dst];
+                                    u64* kd = a.route_keys[dst] + idx * KW;
+#pragma unroll
+                                    for (int i = 0; i < KW; ++i) kd[i] = stash_k[warp][j][i][lane];
+                                    a.route_meta[dst][idx] = stash_m[warp][j][lane];
+                                }
+                                __syncwarp();
+                            } else {
+                                for (u32 dest = 0; dest < a.n_ranks; ++dest) {  // many ranks: one destination at a time
+                                    if (dest == a.rank) continue;
+                                    u32 mine[NB];
+                                    u32 total = 0;
+#pragma unroll
+                                    for (int j = 0; j < NB; ++j) {
+                                        mine[j] = __ballot_sync(0xffffffffu, ((acts >> j) & 1u) && stash_o[warp][j][lane] == dest);
+                                        total += __popc(mine[j]);
+                                    }
+                                    if (total == 0) continue;
+                                    u64 base = 0;
+                                    if (lane == 0) base = atomicAdd(a.route_count + dest, (u64)total);
+                                    base = __shfl_sync(0xffffffffu, base, 0);
+                                    u64* kbase = a.route_keys[dest];
+                                    unsigned short* mbase = a.route_meta[dest];
+#pragma unroll
+                                    for (int j = 0; j < NB; ++j) {
+                                        if ((mine[j] >> lane) & 1u) {
+                                            const u64 idx = base + __popc(mine[j] & lane_lt);
+#pragma unroll
+                                            for (int i = 0; i < KW; ++i) kbase[idx * KW + i] = stash_k[warp][j][i][lane];
+                                            mbase[idx] = stash_m[warp][j][lane];
+                                        }
+                                        base += __popc(mine[j]);
+                                    }
                                 }
                             }
                         }
