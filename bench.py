@@ -105,19 +105,7 @@ def make_workload(name: str, rank: int, world: int):
     # weak scaling: genome x world, this rank's shard = base.n_reads reads with globally unique ids
     w = synth.Workload(f"{name}x{world}", base.genome_bp * world, base.read_len, base.coverage, base.error, base.k,
                        base.paired, base.seed, base.outer_mean, base.outer_std)
-    parts = []
-    rng_skip = rank  # every rank regenerates the shared genome (same seed) but draws its own reads
-    gen = synth.generate_codes(synth.Workload(w.name, w.genome_bp, w.read_len, w.coverage, w.error, w.k, w.paired, w.seed,
-                                              w.outer_mean, w.outer_std), n_reads=base.n_reads * world)
-    lo, hi = rank * base.n_reads, (rank + 1) * base.n_reads
-    for first, m0, m1 in gen:
-        a, b = max(first, lo), min(first + m0.shape[0], hi)
-        if a < b:
-            parts.append(synth.lines_from_codes(a, m0[a - first: b - first], None if m1 is None else m1[a - first: b - first]))
-        if first + m0.shape[0] >= hi:
-            break
-    del rng_skip
-    return w, np.concatenate(parts), base.n_reads
+    return w, synth.shard_text(w, rank, base.n_reads), base.n_reads
 
 
 def expected_distinct(w, n_reads):
