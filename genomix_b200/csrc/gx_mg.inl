@@ -6,15 +6,56 @@
 // rank owner_of(hash(key)); the extract kernel inserts own keys directly and appends the others to per-owner
 // send buckets; gx_mg_exchange() ships the buckets with one NCCL all-to-all-v (ncclSend/ncclRecv group over
 // NVLink) and upserts what arrives. Read heads travel the same way with their packed sequences.
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types and constants only: the library is bound at run time (see NcclApi)
 
 namespace {
+
+// NCCL is resolved lazily with dlopen instead of being a link-time dependency: a single-GPU job never loads it, and a
+// multi-GPU job binds to the NCCL already in the process (e.g. the one PyTorch ships, which must not be shadowed by a
+// different libnccl.so.2 loaded earlier) or else to the system library.
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+};
+
+NcclApi& nccl_api() {
+    static NcclApi api;
+    if (api.handle || !api.error.empty()) return api;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);   // already in the process?
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { api.error = std::string("cannot load libnccl.so.2: ") + dlerror(); return api; }
+    auto sym = [&](const char* name) { void* p = dlsym(h, name); if (!p && api.error.empty()) api.error = std::string("NCCL symbol missing: ") + name; return p; };
+    api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+    api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+    api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+    api.Send = (decltype(api.Send))sym("ncclSend");
+    api.Recv = (decltype(api.Recv))sym("ncclRecv");
+    api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+    api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+    api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+    if (api.error.empty()) api.handle = h;
+    return api;
+}
 
 #define NCCL_TRY(c, expr)                                                                        \
     do {                                                                                         \
         ncclResult_t r__ = (expr);                                                               \
         if (r__ != ncclSuccess)                                                                  \
-            return fail(c, GX_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, ncclGetErrorString(r__), __FILE__, __LINE__); \
+            return fail(c, GX_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, nccl_api().GetErrorString(r__), __FILE__, __LINE__); \
     } while (0)
 
 struct MgState {
@@ -98,7 +139,7 @@ void mg_destroy(gx_ctx* c) {
     MgState* m = mg_of(c);
     if (!m) return;
     if (m->comm_stream) cudaStreamSynchronize(m->comm_stream);
-    if (m->comm) ncclCommDestroy(m->comm);
+    if (m->comm) nccl_api().CommDestroy(m->comm);
     if (m->comm_stream) cudaStreamDestroy(m->comm_stream);
     if (m->ev_ready) cudaEventDestroy(m->ev_ready);
     for (auto e : m->ev_step) if (e) cudaEventDestroy(e);
@@ -127,7 +168,7 @@ extern "C" {
 int gx_mg_unique_id(uint8_t out_id[128]) {
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
     ncclUniqueId id;
-    if (ncclGetUniqueId(&id) != ncclSuccess) return GX_ERR_CUDA;
+    if (!nccl_api().handle || nccl_api().GetUniqueId(&id) != ncclSuccess) return GX_ERR_CUDA;
     memcpy(out_id, &id, 128);
     return GX_OK;
 }
@@ -136,6 +177,7 @@ int gx_mg_init(gx_ctx* c, const uint8_t id_bytes[128]) {
     GX_TRY(require_live(c));
     if (c->cfg.n_ranks < 2) return fail(c, GX_ERR_INVALID, "gx_mg_init on a single-rank ctx");
     if (c->mg) return fail(c, GX_ERR_STATE, "gx_mg_init called twice");
+    if (!nccl_api().handle) return fail(c, GX_ERR_CUDA, "NCCL unavailable: %s", nccl_api().error.c_str());
     cudaSetDevice(c->cfg.device);
     MgState* m = new MgState();
     c->mg = m;
@@ -144,7 +186,7 @@ int gx_mg_init(gx_ctx* c, const uint8_t id_bytes[128]) {
     m->route_keys.resize(m->n); m->route_meta.resize(m->n); m->send_heads.resize(m->n); m->send_store.resize(m->n);
     ncclUniqueId id;
     memcpy(&id, id_bytes, 128);
-    NCCL_TRY(c, ncclCommInitRank(&m->comm, m->n, id, m->rank));
+    NCCL_TRY(c, nccl_api().CommInitRank(&m->comm, m->n, id, m->rank));
     {   // highest priority: NCCL's copy CTAs get the next free SM slots while the upsert kernel is running
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -200,7 +242,7 @@ int gx_mg_exchange(gx_ctx* c) {
         GX_TRY(check_launch(c, "route_heads"));
     }
     // ---- 2. everybody learns everybody's counts
-    NCCL_TRY(c, ncclAllGather(m->counts.p, m->all_counts.p, (size_t)3 * n, ncclUint64, m->comm, c->stream));
+    NCCL_TRY(c, nccl_api().AllGather(m->counts.p, m->all_counts.p, (size_t)3 * n, ncclUint64, m->comm, c->stream));
     std::vector<u64> all((size_t)3 * n * n);
     CUDA_TRY(c, cudaMemcpyAsync(all.data(), m->all_counts.p, all.size() * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -236,7 +278,7 @@ int gx_mg_exchange(gx_ctx* c) {
                     if (mp) { cudaIpcCloseMemHandle(mp); mp = nullptr; }
                 }
             }
-            NCCL_TRY(c, ncclAllReduce(m->token.p, m->token.p, 1, ncclFloat, ncclSum, m->comm, c->stream));  // everyone closed
+            NCCL_TRY(c, nccl_api().AllReduce(m->token.p, m->token.p, 1, ncclFloat, ncclSum, m->comm, c->stream));  // everyone closed
             CUDA_TRY(c, cudaStreamSynchronize(c->stream));
             struct Pub { cudaIpcMemHandle_t h[4]; u64 cap[4]; };
             Pub mine;
@@ -257,7 +299,7 @@ int gx_mg_exchange(gx_ctx* c) {
             }
             GX_TRY(ensure(c, m->pub_dev, sizeof(Pub) * (size_t)(n + 1)));
             CUDA_TRY(c, cudaMemcpyAsync(m->pub_dev.p, &mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
-            NCCL_TRY(c, ncclAllGather(m->pub_dev.p, (uint8_t*)m->pub_dev.p + sizeof(Pub), sizeof(Pub), ncclUint8, m->comm, c->stream));
+            NCCL_TRY(c, nccl_api().AllGather(m->pub_dev.p, (uint8_t*)m->pub_dev.p + sizeof(Pub), sizeof(Pub), ncclUint8, m->comm, c->stream));
             std::vector<Pub> pubs(n);
             CUDA_TRY(c, cudaMemcpyAsync(pubs.data(), (uint8_t*)m->pub_dev.p + sizeof(Pub), sizeof(Pub) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
             CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -303,17 +345,17 @@ int gx_mg_exchange(gx_ctx* c) {
                 uint8_t* dst = (uint8_t*)m->peer_ptr[(size_t)to * 4 + kind] + (size_t)seg_off(me, kind, to) * unit_bytes(kind);
                 CUDA_TRY(c, cudaMemcpyAsync(dst, src[kind], bytes, cudaMemcpyDeviceToDevice, m->comm_stream));
             }
-            NCCL_TRY(c, ncclAllReduce(m->token.p, m->token.p, 1, ncclFloat, ncclSum, m->comm, m->comm_stream));
+            NCCL_TRY(c, nccl_api().AllReduce(m->token.p, m->token.p, 1, ncclFloat, ncclSum, m->comm, m->comm_stream));
         } else {
-            NCCL_TRY(c, ncclGroupStart());
+            NCCL_TRY(c, nccl_api().GroupStart());
             for (int kind = 0; kind < 4; ++kind) {
                 const size_t sb = (size_t)count_kind(me, kind, to) * unit_bytes(kind);
-                if (sb) NCCL_TRY(c, ncclSend(src[kind], sb, ncclUint8, to, m->comm, m->comm_stream));
+                if (sb) NCCL_TRY(c, nccl_api().Send(src[kind], sb, ncclUint8, to, m->comm, m->comm_stream));
                 const size_t rb = (size_t)count_kind(from, kind, me) * unit_bytes(kind);
-                if (rb) NCCL_TRY(c, ncclRecv((uint8_t*)m->inbox[kind].p + (size_t)seg_off(from, kind, me) * unit_bytes(kind), rb, ncclUint8,
+                if (rb) NCCL_TRY(c, nccl_api().Recv((uint8_t*)m->inbox[kind].p + (size_t)seg_off(from, kind, me) * unit_bytes(kind), rb, ncclUint8,
                                              from, m->comm, m->comm_stream));
             }
-            NCCL_TRY(c, ncclGroupEnd());
+            NCCL_TRY(c, nccl_api().GroupEnd());
         }
         CUDA_TRY(c, cudaEventRecord(m->ev_step[i], m->comm_stream));
         m->exchanged += cnt(me, 0, to);
@@ -372,7 +414,7 @@ int gx_mg_exchange(gx_ctx* c) {
     if (m->use_ipc) {
         // nobody may reuse (overwrite) its send buckets or inbox before every rank has finished reading: arrival barriers
         // ordered the copies, this final one orders the end of the upserts that read the inboxes
-        NCCL_TRY(c, ncclAllReduce(m->token.p, m->token.p, 1, ncclFloat, ncclSum, m->comm, c->stream));
+        NCCL_TRY(c, nccl_api().AllReduce(m->token.p, m->token.p, 1, ncclFloat, ncclSum, m->comm, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     }
     return GX_OK;

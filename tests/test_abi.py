@@ -76,3 +76,12 @@ def test_kmer_string_helpers():
         s = "".join(rng.choice(list("ACGT"), size=k))
         assert T.string_to_kmer(s) == O.kmer_from_string_bytes(k, s.encode(), 0)
         assert T.kmer_to_string(k, T.string_to_kmer(s)) == s
+
+
+def test_header_is_plain_c(tmp_path):
+    """the boundary is a C ABI: the header must compile as C (no C++ or torch types in the signatures)"""
+    import subprocess
+    src = tmp_path / "t.c"
+    src.write_text('#include "genomix_gb.h"\nint main(void) { gx_config c; gx_stats s; gx_graph_stats g; (void)c; (void)s; (void)g; '
+                   'return sizeof(c) + sizeof(s) + sizeof(g) == 0; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)])

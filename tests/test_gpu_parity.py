@@ -292,3 +292,47 @@ def test_graph_statistics_match_reference_definitions():
             want["tips_one"] += (in_deg == 0) != (out_deg == 0)
         assert got == want, k
         assert want["self_edges"] != [0, 0, 0, 0]
+
+
+@pytest.mark.parametrize("k", [31, 55, 91, 128])
+def test_hot_keys_under_contention(k):
+    """thousands of identical and low-complexity reads: every warp hammers the same few slots (CAS races on insertion,
+    the claim/publish protocol of KW >= 3 spinning on LOCK, RED.ADD/RED.OR on one value word)"""
+    gx = _gx()
+    rng = np.random.default_rng(k)
+    base = bytes(rng.choice(list(b"ACGT"), size=k + 30).tolist())
+    lines = []
+    for i in range(6000):
+        r = base if i % 3 else b"A" * (k + 20)
+        if i % 7 == 0:
+            r = r[: k + 5]
+        lines.append(b"%d\t%s" % (4 * i + 2, r))
+    text = b"\n".join(lines) + b"\n"
+    got, _ = gpu_canonical(k, text)
+    assert got == oracle_canonical_c(k, text)
+
+
+def test_reset_and_small_record_batches():
+    """gx_reset reuses the allocations for a new job; gx_next_records with a small buffer returns whole records only"""
+    gx = _gx()
+    rng = np.random.default_rng(99)
+    t1 = random_reads_text(rng, 300, 40, 80, paired=True)
+    t2 = random_reads_text(rng, 200, 30, 50)
+    with gx.GraphBuilder(21) as gb:
+        gb.push_lines(t1)
+        gb.finish()
+        whole = gb.records()
+        parts = list(gb.iter_record_batches(batch_bytes=700))
+        assert len(parts) > 10 and b"".join(parts) == whole
+        for p in parts:
+            assert sum(8 + len(k_) + len(v) for k_, v in gx.types.iter_records(p)) == len(p)   # no record is cut
+        with pytest.raises(gx.GenomixError):
+            list(gb.iter_record_batches(batch_bytes=16))
+        assert gx.types.canonical_records(whole) == oracle_canonical(21, t1)
+        with pytest.raises(gx.GenomixError):
+            gb.push_lines(t2)                     # finished job: must reset first
+        gb.reset()
+        gb.push_lines(t2)
+        gb.finish()
+        assert gx.types.canonical_records(gb.records()) == oracle_canonical(21, t2)
+        assert gb.stats()["lines"] == 200
