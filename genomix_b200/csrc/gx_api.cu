@@ -1042,8 +1042,12 @@ int gx_write_sequence_file(gx_ctx* c, const char* path, const uint8_t* sync16, i
     if (!c->finished) return fail(c, GX_ERR_STATE, "gx_write_sequence_file before gx_finish");
     if (!path || n_parts < 0 || (n_parts > 0 && (part < 0 || part >= n_parts))) return fail(c, GX_ERR_INVALID, "bad argument");
     cudaSetDevice(c->cfg.device);
+    // stream the records through a pinned slab (allocated first so that no early return can leak the file handle)
+    const size_t SLAB = 64ull << 20;
+    uint8_t* slab = nullptr;
+    CUDA_TRY(c, cudaMallocHost((void**)&slab, SLAB));
     FILE* f = fopen(path, "wb");
-    if (!f) return fail(c, GX_ERR_INVALID, "cannot open %s for writing", path);
+    if (!f) { cudaFreeHost(slab); return fail(c, GX_ERR_INVALID, "cannot open %s for writing", path); }
     uint8_t sync[16];
     if (sync16) memcpy(sync, sync16, 16);
     else {  // hadoop uses an MD5 of a fresh UID + time; any 16 bytes are valid -- derive them from the path
@@ -1070,10 +1074,6 @@ int gx_write_sequence_file(gx_ctx* c, const char* path, const uint8_t* sync16, i
     put(sync, 16);
     const uint8_t escape[4] = {0xff, 0xff, 0xff, 0xff};
     auto be32 = [](const uint8_t* p) { return ((u32)p[0] << 24) | ((u32)p[1] << 16) | ((u32)p[2] << 8) | (u32)p[3]; };
-    // stream the records through a pinned slab
-    const size_t SLAB = 64ull << 20;
-    uint8_t* slab = nullptr;
-    CUDA_TRY(c, cudaMallocHost((void**)&slab, SLAB));
     int rc = GX_OK;
     u64 cursor = 0;
     while (cursor < c->record_bytes && io_ok) {
