@@ -119,19 +119,6 @@ __device__ __forceinline__ void pack_read_to_store(const uint8_t* __restrict__ s
     }
 }
 
-// Edge-mask bits of one occurrence, exactly as setEdgesForCurAndNext assigns them
-// (ReadsKeyValueParserFactory.java:209-233) seen from the canonical key (gx_internal.cuh header):
-//   to next  : cur F -> FF/FR with base b;      cur R -> RF/RR with base 3-b
-//   from prev: cur F -> RR/RF with base a;      cur R -> FR/FF with base 3-a
-__device__ __forceinline__ u32 edge_bit_next(bool cur_rev, bool next_rev, u32 b) {
-    const u32 type = cur_rev ? (next_rev ? 3u : 2u) : (next_rev ? 1u : 0u);
-    return 1u << (type * 4u + (cur_rev ? 3u - b : b));
-}
-__device__ __forceinline__ u32 edge_bit_prev(bool cur_rev, bool prev_rev, u32 a) {
-    const u32 type = cur_rev ? (prev_rev ? 0u : 1u) : (prev_rev ? 2u : 3u);
-    return 1u << (type * 4u + (cur_rev ? 3u - a : a));
-}
-
 // An upsert that ran out of probe budget: park the record; only if even the spill area is full is the job lost.
 template <int KW>
 __device__ __forceinline__ void spill_record(Counters* ctr, const u64 (&key)[KW], u32 mask) {

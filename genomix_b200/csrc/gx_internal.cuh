@@ -177,6 +177,19 @@ __host__ __device__ __forceinline__ void neighbour_key(const u64 (&x)[KW], int k
     }
 }
 
+// Edge-mask bits of one occurrence, exactly as setEdgesForCurAndNext assigns them
+// (ReadsKeyValueParserFactory.java:209-233) seen from the canonical key (gx_internal.cuh header):
+//   to next  : cur F -> FF/FR with base b;      cur R -> RF/RR with base 3-b
+//   from prev: cur F -> RR/RF with base a;      cur R -> FR/FF with base 3-a
+__host__ __device__ __forceinline__ u32 edge_bit_next(bool cur_rev, bool next_rev, u32 b) {
+    const u32 type = cur_rev ? (next_rev ? 3u : 2u) : (next_rev ? 1u : 0u);
+    return 1u << (type * 4u + (cur_rev ? 3u - b : b));
+}
+__host__ __device__ __forceinline__ u32 edge_bit_prev(bool cur_rev, bool prev_rev, u32 a) {
+    const u32 type = cur_rev ? (prev_rev ? 0u : 1u) : (prev_rev ? 2u : 3u);
+    return 1u << (type * 4u + (cur_rev ? 3u - a : a));
+}
+
 // ASCII -> 2-bit code (A0 C1 G2 T3, either case; GeneCode.java:29-50); ok=false for anything else (code 0)
 __host__ __device__ __forceinline__ u32 code_of(u32 c, bool& ok) {
     const u32 u = c | 0x20u;
