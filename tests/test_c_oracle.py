@@ -61,3 +61,54 @@ def test_java_partition_matches():
     for _ in range(200):
         key = bytes(rng.integers(0, 256, size=int(rng.integers(1, 24)), dtype=np.uint8).tolist())
         assert lib.gxo_java_partition(key, len(key), 13) == O.java_partition(key, 13)
+
+
+def test_differential_fuzz_python_vs_c_oracle():
+    """random small inputs incl. malformed lines, invalid letters, empty fields, CRLF: both restatements must agree on the
+    graph, or both must fail with the same error class at the same line"""
+    rng = np.random.default_rng(2024)
+    alphabet = list(b"ACGTacgtN")
+    status_of = {"format": -4, "NumberFormat": -5, "larger than the read": -6, "lose some of its bits": -7}
+    n_err = n_ok = 0
+    for trial in range(120):
+        k = int(rng.integers(1, 9))
+        lines = []
+        for i in range(int(rng.integers(1, 8))):
+            kind = int(rng.integers(0, 12))
+            seq = bytes(rng.choice(alphabet[:8] if kind else alphabet, size=int(rng.integers(k + 1, k + 12))).tolist())
+            mate = bytes(rng.choice(alphabet[:8], size=int(rng.integers(k + 1, k + 12))).tolist())
+            rid = b"%d" % (4 * i + 2)
+            if kind == 1:
+                line = rid + b"\t" + seq + b"\t" + mate
+            elif kind == 2:
+                line = rid + b"\t" + seq + b"\t"             # trailing empty field is dropped
+            elif kind == 3:
+                line = rid + b"\t\t" + mate                  # empty mate 0
+            elif kind == 4 and trial % 3 == 0:
+                line = rid                                   # too few fields
+            elif kind == 5 and trial % 3 == 0:
+                line = b"x" + rid + b"\t" + seq              # bad number
+            elif kind == 6 and trial % 3 == 0:
+                line = rid + b"\t" + seq[:k]                 # k >= length
+            elif kind == 7 and trial % 3 == 0:
+                line = b"%d\t" % ((1 << 29) + i) + seq       # id loses bits
+            else:
+                line = rid + b"\t" + seq
+            lines.append(line)
+        text = (b"\r\n" if trial % 5 == 0 else b"\n").join(lines) + (b"\n" if trial % 2 else b"")
+        try:
+            want = py_canon(k, text)
+            err = None
+        except O.GraphBuildError as e:
+            want, err = None, str(e)
+        if err is None:
+            recs, _ = CO.build_graph_records(k, text, 1 + trial % 3)
+            assert canon(recs) == want
+            n_ok += 1
+        else:
+            with pytest.raises(CO.OracleError) as ei:
+                CO.build_graph_records(k, text, 1)
+            expected = [v for key, v in status_of.items() if key in err]
+            assert expected and ei.value.status == expected[0], (err, ei.value.status)
+            n_err += 1
+    assert n_ok > 40 and n_err > 10
