@@ -256,7 +256,7 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     job_bytes, insert_bytes, b_occ, b_dist = algorithmic_bytes(w.k, w.read_len, n_occ, stats["distinct_kmers"])
-    insert_ms = phase_acc.get("insert", 0.0) / args.steps
+    insert_ms = (phase_acc.get("insert", 0.0) + phase_acc.get("split", 0.0)) / args.steps
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):

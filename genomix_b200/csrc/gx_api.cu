@@ -35,19 +35,29 @@ const EngineOps* engine_ops(int kw) {
 
 namespace {
 
-constexpr double GROW_LOAD = 0.70;    // never let distinct + incoming exceed this fraction of capacity
-constexpr double TARGET_LOAD = 0.50;  // capacity chosen for this load
-constexpr u64 MIN_CAPACITY = 1ull << 16;
-constexpr size_t DEFAULT_CHUNK = 64ull << 20;
-constexpr size_t REGION_BYTES = 32ull << 20;            // table region kept L2-resident by the blocked build
-constexpr size_t BLOCKED_MIN_TABLE_BYTES = 192ull << 20;  // smaller tables are L2-friendly enough for the direct build
+constexpr double MAX_LOAD = 0.75;     // the table never holds more keys than this fraction of its capacity
+constexpr double TARGET_LOAD = 0.60;  // capacity chosen for this load when the number of keys is known or estimated
+constexpr u64 MIN_CAPACITY = 1ull << 20;
+constexpr size_t DEFAULT_CHUNK = 256ull << 20;
+constexpr size_t REGION_BYTES = 32ull << 20;   // table region kept L2-resident while it is being upserted
 
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
 };
 
-enum Phase { PH_PARSE = 0, PH_INSERT = 1, PH_EXCHANGE = 2, PH_FINISH = 3, PH_H2D = 4, PH_XCOMM = 5, PH_XINSERT = 6, PH_COUNT = 8 };
+// One chunk's k-mer records, sorted by bucket = (owner rank, table region); see gx_split.cuh.
+struct Arena {
+    DevBuf keys, meta;          // [occ] records: KW key words, 16-bit edge mask
+    DevBuf seg_start;           // u64 [n_buckets + 1] record index of each bucket's first record
+    DevBuf cursor;              // u64 [n_buckets * CURSOR_PAD] placement cursors
+    DevBuf bucket_count;        // u64 [n_buckets]
+    u64 occ = 0;
+    u32 n_regions = 0;
+    std::vector<u64> owner_off; // host copy of seg_start[o * n_regions], o = 0..n_ranks (multi-GPU only)
+};
+
+enum Phase { PH_PARSE = 0, PH_INSERT = 1, PH_EXCHANGE = 2, PH_FINISH = 3, PH_H2D = 4, PH_XCOMM = 5, PH_XINSERT = 6, PH_SPLIT = 7, PH_COUNT = 8 };
 
 struct PendingTimer {
     int phase;
@@ -72,15 +82,21 @@ struct gx_ctx {
     u64 capacity = 0;
     bool table_live = false;  // false: allocation kept from before gx_reset, content stale
     u64 grows = 0;
+    u64 min_capacity = MIN_CAPACITY;
+    bool keys_estimated = false;   // the capacity already accounts for an estimate of this job's keys (hint or pilot)
+    bool test_start_small = false; // test hook: no hint, no pilot -> the table starts at min_capacity and grows by deferral
 
     DevBuf heads, store;
     DevBuf text, nl_pos, nl_pos2, desc, tile_sums;
     DevBuf hslot, hcount, hstart, hperm, tile_bytes, tile_nodes, records, rec_offsets, parts, dense;
-    DevBuf flat_keys, flat_meta, part_keys, part_meta, bucket_count;  // L2-blocked build
     DevBuf gstats;
     EmitArgs last_emit{};      // arguments of the last emit (dense node list etc.), reused by gx_graph_statistics
-    int blocked_mode = 0;      // 0 auto, 1 never, 2 always (cfg.reserved[2]; tests and A/B runs)
-    u32 blocked_buckets = 0;   // 0 auto (cfg.reserved[3])
+
+    // build
+    Arena arena;               // single GPU: the current chunk's records (reused chunk after chunk)
+    u32 fixed_regions = 0;     // != 0: table regions per rank for the whole job (multi-GPU, or cfg.reserved[3])
+    DevBuf tile_prefix, deferred[2];
+    u64 upserted_records = 0;
 
     u64 global_lines = 0;
     u64 n_nodes = 0, record_bytes = 0;
@@ -93,16 +109,11 @@ struct gx_ctx {
     u64 frame_byte_cursor = 0, frame_rec_cursor = 0;
 
     void* mg = nullptr;  // MgState (gx_mg.inl) when n_ranks > 1
-    cudaStream_t aux_stream = nullptr;   // L2 prefetch of the next table region (blocked build)
-    cudaEvent_t aux_event = nullptr;
 
-    // spill area (two buffers, swapped while one is being re-inserted) and the new-key predictor
-    DevBuf spill_keys[2], spill_meta[2];
+    // spill area (two buffers, swapped while one is being re-inserted)
+    DevBuf spill_keys[2], spill_meta[2], spill_counts[2];
     int spill_cur = 0;
     u64 spill_cap = 0;
-    bool test_no_new_keys = false;
-    double new_key_ratio = -1.0;   // new keys per occurrence in the last measured interval (< 0: unknown)
-    u64 ratio_distinct0 = 0, ratio_pending_occ = 0;
 
     float phase_ms[PH_COUNT] = {0};
     std::vector<PendingTimer> timers;
@@ -115,7 +126,7 @@ namespace {
 thread_local std::string g_create_error;
 
 // multi-GPU hooks, defined in gx_mg.inl
-int mg_prepare_route(gx_ctx* c, u64 incoming, ExtractArgs& a);
+int mg_stage_chunk(gx_ctx* c, const uint8_t* d_text, size_t n, u64 n_lines, u64 chunk_occ);
 int mg_pending(gx_ctx* c, u64* pending);
 int mg_reset(gx_ctx* c);
 void mg_destroy(gx_ctx* c);
@@ -167,6 +178,10 @@ void release(DevBuf& b) {
     if (b.p) cudaFree(b.p);
     b.p = nullptr;
     b.cap = 0;
+}
+
+void release_arena(Arena& a) {
+    release(a.keys); release(a.meta); release(a.seg_start); release(a.cursor); release(a.bucket_count);
 }
 
 cudaEvent_t get_event(gx_ctx* c) {
@@ -249,6 +264,14 @@ int line_error_to_status(gx_ctx* c, u64 packed) {
     return c->sticky;
 }
 
+// ---- table life cycle ---------------------------------------------------------------------------------------
+// Capacity policy. The table never holds more than MAX_LOAD * capacity keys, by construction: the region upsert
+// postpones ("defers") work items once the key count reaches a limit that leaves room for everything in flight, and the
+// host grows the table and re-launches the deferred items (run_upsert). Everything else only tunes speed:
+//   * cfg.expected_kmers, if given, sizes the first allocation for TARGET_LOAD;
+//   * otherwise the first region of a chunk is upserted as a pilot: regions are uniform hash ranges, so its new keys
+//     times the number of regions estimate the chunk's new keys, and the table is sized once for that;
+//   * a table kept across gx_reset is reused as it is.
 int alloc_table(gx_ctx* c, u64 capacity, u64** out) {
     void* p = nullptr;
     const size_t bytes = (size_t)capacity * c->ops->slot_bytes;
@@ -259,80 +282,35 @@ int alloc_table(gx_ctx* c, u64 capacity, u64** out) {
     return GX_OK;
 }
 
-// Capacity policy. The table never holds more than GROW_LOAD * capacity keys: before a batch of inserts the
-// host asks for `room` (how many NEW keys may still arrive) and sizes the batch to it, so the bound holds even
-// if every occurrence of the batch is a new key; high-coverage data keeps re-using the same room. The table is
-// doubled (rehash) only when the room drops under capacity/8 or under `min_room`.
-//   distinct : keys in the table now (Counters::distinct after a sync)
-//   hint     : expected number of further occurrences (sizes the very first allocation only)
-int reserve_room(gx_ctx* c, u64 distinct, u64 min_room, u64 hint, u64* room) {
+int ensure_table(gx_ctx* c, u64 min_capacity) {
     if (c->table && !c->table_live) {
-        // allocation kept across gx_reset: re-initialise and reuse (it is grown below if it turns out too small)
-        c->ops->init_table(c->table, c->capacity, c->stream);
-        GX_TRY(check_launch(c, "init_table"));
-        c->table_live = true;
+        if (c->capacity >= min_capacity) {
+            // allocation kept across gx_reset: re-initialise and reuse
+            c->ops->init_table(c->table, c->capacity, c->stream);
+            GX_TRY(check_launch(c, "init_table"));
+            c->table_live = true;
+            return GX_OK;
+        }
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        CUDA_TRY(c, cudaFree(c->table));
+        c->table = nullptr;
+        c->capacity = 0;
     }
     if (!c->table) {
-        u64 ncap = std::max<u64>(MIN_CAPACITY, c->cfg.expected_kmers ? (u64)((double)c->cfg.expected_kmers / TARGET_LOAD) + 1
-                                                                     : hint + 1);
-        GX_TRY(alloc_table(c, ncap, &c->table));
-        c->capacity = ncap;
+        GX_TRY(alloc_table(c, min_capacity, &c->table));
+        c->capacity = min_capacity;
         c->table_live = true;
     }
-    for (;;) {
-        const u64 limit = (u64)(GROW_LOAD * (double)c->capacity);
-        const u64 have = limit > distinct ? limit - distinct : 0;
-        if (have >= std::max<u64>(c->capacity / 8, std::max<u64>(min_room, 1))) { *room = have; return GX_OK; }
-        const u64 ncap = c->capacity * 2;
-        u64* nt = nullptr;
-        GX_TRY(alloc_table(c, ncap, &nt));
-        c->ops->rehash(c->table, c->capacity, nt, ncap, c->stream);
-        GX_TRY(check_launch(c, "rehash"));
-        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-        if (c->aux_stream) CUDA_TRY(c, cudaStreamSynchronize(c->aux_stream));  // a region prefetch may still read the old table
-        CUDA_TRY(c, cudaFree(c->table));
-        ++c->grows;
-        c->table = nt;
-        c->capacity = ncap;
-    }
-}
-
-// ---- new-key predictor --------------------------------------------------------------------------------------
-// Every occurrence could be a new key, but in sequencing data most are repeats (coverage). After each counter sync
-// the host measures new keys per occurrence over the batches launched since the previous sync and sizes the next
-// batch for twice that rate plus a margin. If the prediction is too low the table runs past GROW_LOAD; should it
-// actually fill up, upserts spill (Counters::spill_*) and handle_spills() grows the table and re-inserts them.
-void note_sync(gx_ctx* c, u64 distinct_now) {
-    if (c->ratio_pending_occ) {
-        c->new_key_ratio = (double)(distinct_now - c->ratio_distinct0) / (double)c->ratio_pending_occ;
-        c->ratio_pending_occ = 0;
-    }
-    c->ratio_distinct0 = distinct_now;
-}
-u64 predict_new_keys(const gx_ctx* c, u64 occ) {
-    if (c->test_no_new_keys) return occ ? 1 : 0;
-    if (c->new_key_ratio < 0) return occ;
-    const double p = 2.0 * c->new_key_ratio * (double)occ + (double)occ / 64.0 + 65536.0;
-    return p >= (double)occ ? occ : (u64)p;
-}
-
-int set_spill_target(gx_ctx* c) {
-    struct { u64 count, cap; u64* keys; unsigned short* meta; } t = {0, c->spill_cap, (u64*)c->spill_keys[c->spill_cur].p,
-                                                                     (unsigned short*)c->spill_meta[c->spill_cur].p};
-    static_assert(offsetof(Counters, spill_meta) - offsetof(Counters, spill_count) == 24, "spill fields are contiguous");
-    CUDA_TRY(c, cudaMemcpyAsync(&c->d_ctr->spill_count, &t, sizeof t, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return GX_OK;
 }
 
-int grow_table(gx_ctx* c) {
-    const u64 ncap = c->capacity * 2;
+// rehash into a table of `ncap` slots (ncap > capacity)
+int grow_table_to(gx_ctx* c, u64 ncap) {
     u64* nt = nullptr;
     GX_TRY(alloc_table(c, ncap, &nt));
-    c->ops->rehash(c->table, c->capacity, nt, ncap, c->stream);
+    c->ops->rehash(c->table, c->capacity, nt, ncap, (u32)c->cfg.n_ranks, c->d_ctr, c->stream);
     GX_TRY(check_launch(c, "rehash"));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    if (c->aux_stream) CUDA_TRY(c, cudaStreamSynchronize(c->aux_stream));
     CUDA_TRY(c, cudaFree(c->table));
     ++c->grows;
     c->table = nt;
@@ -340,7 +318,18 @@ int grow_table(gx_ctx* c) {
     return GX_OK;
 }
 
-// Call after sync_counters(): re-insert records that spilled because the table was fuller than predicted.
+int set_spill_target(gx_ctx* c) {
+    struct { u64 count, cap; u64* keys; unsigned short* meta; u32* counts; } t = {
+        0, c->spill_cap, (u64*)c->spill_keys[c->spill_cur].p, (unsigned short*)c->spill_meta[c->spill_cur].p,
+        (u32*)c->spill_counts[c->spill_cur].p};
+    static_assert(offsetof(Counters, spill_counts) - offsetof(Counters, spill_count) == 32, "spill fields are contiguous");
+    CUDA_TRY(c, cudaMemcpyAsync(&c->d_ctr->spill_count, &t, sizeof t, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return GX_OK;
+}
+
+// Call after sync_counters(): re-insert records whose upsert ran out of probe budget (a last line of defence: with the
+// load bounded by MAX_LOAD probe sequences are short, so this only triggers on adversarial clustering).
 int handle_spills(gx_ctx* c) {
     while (c->h_ctr->spill_count > 0) {
         if (c->h_ctr->table_overflow)
@@ -350,181 +339,168 @@ int handle_spills(gx_ctx* c) {
         const int old = c->spill_cur;
         c->spill_cur ^= 1;
         GX_TRY(set_spill_target(c));   // new spills (from the re-insertion itself) go to the other buffer
-        GX_TRY(grow_table(c));
-        c->ops->insert_records((const u64*)c->spill_keys[old].p, (const unsigned short*)c->spill_meta[old].p, nullptr, n, c->table,
-                               c->capacity, c->d_ctr, c->stream);
+        GX_TRY(grow_table_to(c, c->capacity * 2));
+        c->ops->insert_records((const u64*)c->spill_keys[old].p, (const unsigned short*)c->spill_meta[old].p,
+                               (const u32*)c->spill_counts[old].p, n, c->table, c->capacity, (u32)c->cfg.n_ranks, c->d_ctr, c->stream);
         GX_TRY(check_launch(c, "insert_records"));
-        c->new_key_ratio = -1.0;       // the predictor was wrong: be conservative until re-measured
         GX_TRY(sync_counters(c));
     }
     return GX_OK;
 }
 
-// Insert `n` (key, mask) records that are already grouped by table region (bucket b = records
-// [offsets[b], offsets[b+1])), one launch per region, in groups of regions that fit the table's room.
-int blocked_insert(gx_ctx* c, const u64* keys, const unsigned short* meta, const std::vector<u64>& offsets, u64 distinct) {
-    const u32 n_buckets = (u32)offsets.size() - 1;
-    u64 max_bucket = 1;
-    for (u32 b = 0; b < n_buckets; ++b) max_bucket = std::max<u64>(max_bucket, offsets[b + 1] - offsets[b]);
-    for (u32 b = 0; b < n_buckets;) {
-        u64 room = 0;
-        GX_TRY(reserve_room(c, distinct, max_bucket, offsets[n_buckets], &room));
-        u32 e = b;
-        u64 group = 0;
-        while (e < n_buckets && (e == b || predict_new_keys(c, group + (offsets[e + 1] - offsets[e])) <= room)) {
-            group += offsets[e + 1] - offsets[e];
-            ++e;
-        }
-        c->ratio_pending_occ += group;
-        {
-            ScopedPhase ph(c, PH_INSERT);
-            for (u32 i = b; i < e; ++i) {
-                const u64 cnt = offsets[i + 1] - offsets[i];
-                // while region i is upserted, region i+1 is prefetched into L2 on the auxiliary stream
-                if (c->aux_stream && i + 1 < n_buckets) {
-                    const u64 lo = (u64)(((unsigned __int128)(i + 1) * c->capacity) / n_buckets);
-                    const u64 hi = (u64)(((unsigned __int128)(i + 2) * c->capacity) / n_buckets);
-                    cudaEventRecord(c->aux_event, c->stream);
-                    cudaStreamWaitEvent(c->aux_stream, c->aux_event, 0);
-                    prefetch_region_kernel<<<148, 256, 0, c->aux_stream>>>((const uint8_t*)c->table + lo * c->ops->slot_bytes,
-                                                                           (hi - lo) * c->ops->slot_bytes);
-                    ++c->launches;
-                }
-                if (!cnt) continue;
-                c->ops->insert_records(keys + offsets[i] * c->kw, meta + offsets[i], nullptr, cnt, c->table, c->capacity, c->d_ctr,
-                                       c->stream);
-                GX_TRY(check_launch(c, "insert_records"));
-            }
-        }
-        b = e;
-        if (b < n_buckets) {
-            GX_TRY(sync_counters(c));
-            GX_TRY(handle_spills(c));
-            distinct = c->h_ctr->distinct;
-            note_sync(c, distinct);
-        }
+// ---- build: split + region upsert -----------------------------------------------------------------------------
+// Table regions per rank for a chunk of `occ` occurrences: regions of about REGION_BYTES of the table the job is
+// expected to end up with.
+u32 choose_regions(gx_ctx* c, u64 occ) {
+    const u32 max_regions = (u32)(SP_MAX_BUCKETS / std::max(1, c->cfg.n_ranks));
+    if (c->fixed_regions) return std::min(c->fixed_regions, max_regions);
+    const u64 distinct = c->table_live ? c->h_ctr->distinct : 0;
+    const u64 keys = c->cfg.expected_kmers ? std::max<u64>(c->cfg.expected_kmers, distinct) : distinct + occ;
+    size_t table_bytes = (size_t)((double)keys / TARGET_LOAD) * c->ops->slot_bytes;
+    if (c->table_live) table_bytes = std::max(table_bytes, (size_t)c->capacity * c->ops->slot_bytes);
+    return (u32)std::min<size_t>(max_regions, std::max<size_t>(1, (table_bytes + REGION_BYTES - 1) / REGION_BYTES));
+}
+
+// K1: the chunk's k-mer records into `ar`, sorted by (owner, region). `owner_keys/meta` = nullptr: everything goes to the
+// arena (cursors count from the arena start); else per-owner record areas (cursors count from each owner's block).
+int split_chunk(gx_ctx* c, const uint8_t* d_text, size_t n, u64 n_lines, u64 chunk_occ, u32 n_regions, Arena& ar) {
+    const u32 n_ranks = (u32)c->cfg.n_ranks, n_buckets = n_ranks * n_regions;
+    ar.occ = chunk_occ;
+    ar.n_regions = n_regions;
+    GX_TRY(ensure(c, ar.keys, (size_t)chunk_occ * c->kw * sizeof(u64)));
+    GX_TRY(ensure(c, ar.meta, (size_t)chunk_occ * sizeof(unsigned short)));
+    GX_TRY(ensure(c, ar.seg_start, (size_t)(SP_MAX_BUCKETS + 1) * sizeof(u64)));
+    GX_TRY(ensure(c, ar.cursor, (size_t)SP_MAX_BUCKETS * CURSOR_PAD * sizeof(u64)));
+    GX_TRY(ensure(c, ar.bucket_count, (size_t)SP_MAX_BUCKETS * sizeof(u64)));
+    ScopedPhase ph(c, PH_SPLIT);
+    CUDA_TRY(c, cudaMemsetAsync(ar.bucket_count.p, 0, (size_t)n_buckets * sizeof(u64), c->stream));
+    SplitArgs a{};
+    a.text = d_text; a.n_text = n;
+    a.desc = (const LineDesc*)c->desc.p; a.n_lines = n_lines;
+    a.k = c->k;
+    a.heads = c->heads.p;
+    a.store = (uint8_t*)c->store.p;
+    a.ctr = c->d_ctr;
+    a.n_ranks = n_ranks; a.n_regions = n_regions;
+    a.bucket_count = (u64*)ar.bucket_count.p;
+    a.cursor = (u64*)ar.cursor.p;
+    for (u32 o = 0; o < n_ranks; ++o) { a.owner_keys[o] = (u64*)ar.keys.p; a.owner_meta[o] = (unsigned short*)ar.meta.p; }
+    c->ops->split_count(a, c->stream);
+    GX_TRY(check_launch(c, "split_count"));
+    split_prefix_kernel<<<1, 1024, 0, c->stream>>>((const u64*)ar.bucket_count.p, n_buckets, n_regions, 0, (u64*)ar.seg_start.p,
+                                                   (u64*)ar.cursor.p);
+    GX_TRY(check_launch(c, "split_prefix"));
+    c->ops->split_place(a, c->stream);
+    GX_TRY(check_launch(c, "split_place"));
+    if (getenv("GENOMIX_GB_DEBUG")) {
+        CUDA_TRY(c, cudaMemsetAsync(&c->d_ctr->scratch[0], 0, sizeof(u64), c->stream));
+        c->ops->check_arena((const u64*)ar.keys.p, (const u64*)ar.seg_start.p, n_ranks, n_regions, &c->d_ctr->scratch[0], c->stream);
+        GX_TRY(sync_counters(c));
+        fprintf(stderr, "[genomix_gb debug] split: %llu records, %u regions x %u ranks, %llu records outside their bucket\n",
+                (unsigned long long)chunk_occ, n_regions, n_ranks, (unsigned long long)c->h_ctr->scratch[0]);
     }
     return GX_OK;
 }
 
-// L2-blocked handling of one parsed chunk: pass 1 extract_kernel<EX_FLAT>, pass 2
-// partition_flat_kernel, pass 3 blocked_insert.
-int blocked_chunk(gx_ctx* c, const uint8_t* d_text, size_t n, u64 n_lines, u64 chunk_occ, u32 n_buckets, u64 distinct) {
-    GX_TRY(ensure(c, c->flat_keys, (size_t)chunk_occ * c->kw * sizeof(u64)));
-    GX_TRY(ensure(c, c->flat_meta, (size_t)chunk_occ * sizeof(unsigned short)));
-    GX_TRY(ensure(c, c->part_keys, (size_t)chunk_occ * c->kw * sizeof(u64)));
-    GX_TRY(ensure(c, c->part_meta, (size_t)chunk_occ * sizeof(unsigned short)));
-    GX_TRY(ensure(c, c->bucket_count, (size_t)MAX_BUCKETS * BUCKET_PAD * sizeof(u64)));
-    std::vector<u64> counts(n_buckets), offsets(n_buckets + 1, 0);
-    {
-        ScopedPhase ph(c, PH_INSERT);
-        CUDA_TRY(c, cudaMemsetAsync(c->bucket_count.p, 0, (size_t)n_buckets * BUCKET_PAD * sizeof(u64), c->stream));
-        ExtractArgs a{};
-        a.text = d_text; a.n_text = n;
-        a.desc = (const LineDesc*)c->desc.p; a.n_lines = n_lines;
-        a.k = c->k;
+// K2: upsert regions [r0, r1) of the given record areas; grows the table and re-launches whatever the kernel deferred.
+// Leaves the stream synchronised and c->h_ctr current.
+int run_upsert(gx_ctx* c, const UpsertSrc* src, u32 n_src, u32 n_regions, u32 r0, u32 r1, u64 max_items) {
+    UpsertArgs a{};
+    for (u32 s = 0; s < n_src; ++s) a.src[s] = src[s];
+    a.n_src = n_src; a.r0 = r0; a.r1 = r1; a.n_regions = n_regions; a.n_ranks = (u32)c->cfg.n_ranks;
+    a.ctr = c->d_ctr;
+    const size_t n_pairs = (size_t)(r1 - r0) * n_src;
+    GX_TRY(ensure(c, c->tile_prefix, (n_pairs + 1) * sizeof(u32)));
+    GX_TRY(ensure(c, c->deferred[0], (size_t)max_items * sizeof(u32)));
+    GX_TRY(ensure(c, c->deferred[1], (size_t)max_items * sizeof(u32)));
+    a.item_prefix = (const u32*)c->tile_prefix.p;
+    upsert_prefix_kernel<<<1, 1024, 0, c->stream>>>(a, (u32*)c->tile_prefix.p);
+    GX_TRY(check_launch(c, "upsert_prefix"));
+    int cur = 0;
+    u64 n_deferred = 0;
+    const unsigned ctas_per_sm = c->kw == 1 ? 2 : 1;
+    for (;;) {
         a.table = c->table; a.capacity = c->capacity;
-        a.heads = c->heads.p;
-        a.store = (uint8_t*)c->store.p;
-        a.ctr = c->d_ctr;
-        a.n_ranks = 1; a.rank = 0;
-        a.flat_keys = (u64*)c->flat_keys.p; a.flat_meta = (unsigned short*)c->flat_meta.p;
-        a.bucket_count = (u64*)c->bucket_count.p; a.n_buckets = n_buckets;
-        c->ops->extract_flat(a, c->stream);
-        GX_TRY(check_launch(c, "extract_flat"));
-        CUDA_TRY(c, cudaMemcpy2DAsync(counts.data(), sizeof(u64), c->bucket_count.p, BUCKET_PAD * sizeof(u64), sizeof(u64), n_buckets,
-                                      cudaMemcpyDeviceToHost, c->stream));
+        // Every warp in flight may add an item's worth of keys that ctr->distinct does not show yet, plus what it has not
+        // published (UP_PUBLISH), plus the item it decides on with a count that is one item old: the margin below the load
+        // limit. Small tables get fewer warps so that the margin stays a fraction of the limit.
+        const u64 limit = (u64)(MAX_LOAD * (double)c->capacity);
+        const u64 per_warp = UP_PUBLISH + 2 * UP_ITEM;
+        const u64 warps = std::max<u64>(1, std::min<u64>((u64)148 * ctas_per_sm * UP_WARPS, limit / (4 * per_warp)));
+        const unsigned grid = (unsigned)((warps + UP_WARPS - 1) / UP_WARPS);
+        a.active_warps = (u32)std::min<u64>(UP_WARPS, warps);
+        a.hard_limit = limit - std::min<u64>(limit, (u64)grid * a.active_warps * per_warp);
+        a.deferred_out = (u32*)c->deferred[cur].p;
+        a.deferred_in = n_deferred ? (const u32*)c->deferred[cur ^ 1].p : nullptr;
+        a.n_deferred_in = (u32)n_deferred;
+        c->ops->upsert_regions(a, grid, c->stream);
+        GX_TRY(check_launch(c, "upsert_regions"));
+        GX_TRY(sync_counters(c));
+        GX_TRY(handle_spills(c));
+        n_deferred = c->h_ctr->deferred_count;
+        if (!n_deferred) return GX_OK;
+        // the table reached its load limit: double it and apply what was postponed
+        GX_TRY(grow_table_to(c, c->capacity * 2));
+        CUDA_TRY(c, cudaMemsetAsync(&c->d_ctr->deferred_count, 0, sizeof(u64), c->stream));
+        cur ^= 1;
     }
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    drain_timers(c);
-    for (u32 b = 0; b < n_buckets; ++b) offsets[b + 1] = offsets[b] + counts[b];
-    if (offsets[n_buckets] != chunk_occ)
-        return c->sticky = fail(c, GX_ERR_INVALID, "internal error: flat extract produced %llu of %llu occurrences",
-                                (unsigned long long)offsets[n_buckets], (unsigned long long)chunk_occ);
-    {
-        ScopedPhase ph(c, PH_INSERT);
-        CUDA_TRY(c, cudaMemcpy2DAsync(c->bucket_count.p, BUCKET_PAD * sizeof(u64), offsets.data(), sizeof(u64), sizeof(u64), n_buckets,
-                                      cudaMemcpyHostToDevice, c->stream));
-        c->ops->partition_flat((const u64*)c->flat_keys.p, (const unsigned short*)c->flat_meta.p, chunk_occ, n_buckets,
-                               (u64*)c->bucket_count.p, (u64*)c->part_keys.p, (unsigned short*)c->part_meta.p, c->stream);
-        GX_TRY(check_launch(c, "partition_flat"));
-    }
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // offsets (pageable) were the source of an async copy
-    return blocked_insert(c, (const u64*)c->part_keys.p, (const unsigned short*)c->part_meta.p, offsets, distinct);
 }
 
-// After a parse kernel filled c->desc for `n_lines` lines of the text at d_text: check errors, make room for heads,
-// packed reads and k-mers, then extract + insert.
+// Upsert all regions of `n_src` record areas holding `total` records: capacity policy around run_upsert.
+int upsert_sources(gx_ctx* c, const UpsertSrc* src, u32 n_src, u32 n_regions, u64 total, int phase = PH_INSERT) {
+    if (total == 0) return GX_OK;
+    const u64 max_items = total / UP_ITEM + (u64)n_regions * n_src + 1;
+    if (max_items >= 0xffffffffull) return fail(c, GX_ERR_INVALID, "chunk of %llu k-mer records is too large", (unsigned long long)total);
+    const u64 distinct0 = c->table_live ? c->h_ctr->distinct : 0;
+    const u64 hint = c->test_start_small ? 0 : c->cfg.expected_kmers;
+    if (!c->table_live) {
+        u64 cap = c->min_capacity;
+        if (hint) cap = std::max<u64>(cap, (u64)((double)hint / TARGET_LOAD) + 1);
+        else if (!c->test_start_small) cap = std::max<u64>(cap, n_regions >= 8 ? 4 * (total / n_regions) : (u64)((double)total / TARGET_LOAD) + 1);
+        GX_TRY(ensure_table(c, cap));
+        c->keys_estimated = hint != 0;
+    }
+    u32 r = 0;
+    const bool worst_case_fits = (double)(distinct0 + total) <= MAX_LOAD * (double)c->capacity;
+    const bool trust_hint = hint && distinct0 < hint;
+    if (!worst_case_fits && !trust_hint && !c->test_start_small && n_regions >= 8) {
+        // pilot: region 0 tells how many of this chunk's records are new keys
+        ScopedPhase ph(c, phase);
+        GX_TRY(run_upsert(c, src, n_src, n_regions, 0, 1, max_items));
+        const u64 added = c->h_ctr->distinct - distinct0;
+        const u64 expect = distinct0 + (u64)((double)added * n_regions * 1.03) + 65536;
+        const u64 want = (u64)((double)expect / TARGET_LOAD) + 1;
+        if (want > c->capacity) GX_TRY(grow_table_to(c, want));
+        c->keys_estimated = true;
+        r = 1;
+    }
+    ScopedPhase ph(c, phase);
+    GX_TRY(run_upsert(c, src, n_src, n_regions, r, n_regions, max_items));
+    c->upserted_records += total;
+    return GX_OK;
+}
+
+// After a parse kernel filled c->desc for `n_lines` lines of the text at d_text: check errors, make room for heads and
+// packed reads, then split the chunk's k-mers by table region and upsert them (single GPU) or stage them for the
+// exchange (multi GPU).
 int insert_parsed_chunk(gx_ctx* c, const uint8_t* d_text, size_t n) {
     GX_TRY(sync_counters(c));
     GX_TRY(handle_spills(c));
     const Counters& h = *c->h_ctr;
-    note_sync(c, h.distinct);
     const u64 n_lines = h.chunk_lines;
     c->global_lines += n_lines;
     if (h.error != ~0ull) return line_error_to_status(c, h.error);
     if (h.chunk_reads == 0) return GX_OK;
-    // room for this chunk's heads, packed reads and k-mers
+    // room for this chunk's heads and packed reads
     GX_TRY(ensure(c, c->heads, (size_t)h.head_cursor * c->ops->head_bytes,
                   (size_t)(h.head_cursor - h.chunk_reads) * c->ops->head_bytes, true));
     GX_TRY(ensure(c, c->store, (size_t)h.store_cursor, (size_t)(h.store_cursor - h.chunk_store)));
-    const u64 max_line_occ = std::max<u64>(h.chunk_max_line_occ, 1);
-    u64 distinct = h.distinct, occ_left = h.chunk_occ;
-    // ---- L2-blocked build (single GPU, table much larger than L2): flat extract -> partition by table region ->
-    //      region-by-region insert, so that every table access of the insert is an L2 hit
-    if (c->cfg.n_ranks == 1 && c->blocked_mode != 1) {
-        u64 room = 0;
-        GX_TRY(reserve_room(c, distinct, max_line_occ, h.chunk_occ, &room));
-        const size_t table_bytes = (size_t)c->capacity * c->ops->slot_bytes;
-        // measured on B200 (profiles/r01g): the generic partition pass costs what the random HBM accesses cost, so the
-        // blocked build is opt-in (cfg.reserved[2] == 2) until its partition is fused into the extract kernel
-        if (c->blocked_mode == 2 || (c->blocked_mode == 3 && table_bytes >= BLOCKED_MIN_TABLE_BYTES)) {
-            const u32 n_buckets = c->blocked_buckets ? c->blocked_buckets
-                : (u32)std::min<size_t>(MAX_BUCKETS, std::max<size_t>(2, (table_bytes + REGION_BYTES - 1) / REGION_BYTES));
-            return blocked_chunk(c, d_text, n, n_lines, h.chunk_occ, n_buckets, distinct);
-        }
-    }
-    // ---- direct build: extract + upsert, in as many line ranges as the table's room and the predictor dictate
-    for (u64 line0 = 0; line0 < n_lines;) {
-        u64 room = 0;
-        GX_TRY(reserve_room(c, distinct, max_line_occ, h.chunk_occ, &room));
-        const u64 lines_left = n_lines - line0;
-        const u64 predicted = predict_new_keys(c, occ_left);
-        u64 take = lines_left;
-        if (predicted > room) {
-            take = (u64)((double)lines_left * (double)room / (double)predicted);
-            take = std::min<u64>(lines_left, std::max<u64>(take, std::max<u64>(room / max_line_occ, 1)));
-        }
-        const u64 take_occ = take == lines_left ? occ_left : std::min<u64>(occ_left, (u64)((double)occ_left * (double)take / (double)lines_left) + max_line_occ);
-        ScopedPhase ph(c, PH_INSERT);
-        ExtractArgs a{};
-        a.text = d_text; a.n_text = n;
-        a.desc = (const LineDesc*)c->desc.p + line0; a.n_lines = take;
-        a.k = c->k;
-        a.table = c->table; a.capacity = c->capacity;
-        a.heads = c->heads.p;
-        a.store = (uint8_t*)c->store.p;
-        a.ctr = c->d_ctr;
-        a.n_ranks = 1; a.rank = 0;
-        if (c->cfg.n_ranks > 1) {
-            GX_TRY(mg_prepare_route(c, std::min<u64>(occ_left, take * max_line_occ), a));
-            c->ops->extract_route(a, c->stream);
-            GX_TRY(check_launch(c, "extract_route"));
-        } else {
-            c->ops->extract_insert(a, c->stream);
-            GX_TRY(check_launch(c, "extract_insert"));
-        }
-        c->ratio_pending_occ += take_occ;
-        line0 += take;
-        if (line0 < n_lines) {  // more ranges to go: learn how many keys the last one really added
-            GX_TRY(sync_counters(c));
-            GX_TRY(handle_spills(c));
-            distinct = c->h_ctr->distinct;
-            note_sync(c, distinct);
-            occ_left = occ_left > take_occ ? occ_left - take_occ : std::min<u64>(occ_left, (n_lines - line0) * max_line_occ);
-        }
-    }
-    return GX_OK;
+    const u64 chunk_occ = h.chunk_occ;
+    if (c->cfg.n_ranks > 1) return mg_stage_chunk(c, d_text, n, n_lines, chunk_occ);
+    const u32 n_regions = choose_regions(c, chunk_occ);
+    GX_TRY(split_chunk(c, d_text, n, n_lines, chunk_occ, n_regions, c->arena));
+    UpsertSrc src{(const u64*)c->arena.keys.p, (const unsigned short*)c->arena.meta.p, (const u64*)c->arena.seg_start.p, 0};
+    return upsert_sources(c, &src, 1, n_regions, chunk_occ);
 }
 
 // Line index of text[0, n): fills *nl_buf with the offsets of the line terminators (virtual one for an unterminated
@@ -632,8 +608,8 @@ int gx_create(const gx_config* cfg, gx_ctx** out) {
         return fail(nullptr, GX_ERR_INVALID, "gx_create: kmer_length %d outside [1, %d]", cfg->kmer_length, 32 * GX_MAX_KW);
     if (cfg->sort_output != 0)
         return fail(nullptr, GX_ERR_INVALID, "gx_create: sort_output is not implemented (record order is not observable downstream)");
-    if (cfg->n_ranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->n_ranks)
-        return fail(nullptr, GX_ERR_INVALID, "gx_create: bad rank %d of %d", cfg->rank, cfg->n_ranks);
+    if (cfg->n_ranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->n_ranks || cfg->n_ranks > SP_MAX_RANKS)
+        return fail(nullptr, GX_ERR_INVALID, "gx_create: bad rank %d of %d (at most %d ranks)", cfg->rank, cfg->n_ranks, SP_MAX_RANKS);
     int n_dev = 0;
     cudaError_t e = cudaGetDeviceCount(&n_dev);
     if (e != cudaSuccess || n_dev == 0)
@@ -654,23 +630,20 @@ int gx_create(const gx_config* cfg, gx_ctx** out) {
     c->kw = (c->k + 31) / 32;
     c->ops = engine_ops(c->kw);
     if (cfg->reserved[0]) c->chunk_bytes = (size_t)cfg->reserved[0];
-    c->blocked_mode = (int)(cfg->reserved[2] & 0xff);
-    c->test_no_new_keys = (cfg->reserved[2] >> 8) & 1;  // test hook: predictor claims nothing is new -> exercises spills
-    c->blocked_buckets = (u32)std::min<u64>(cfg->reserved[3], MAX_BUCKETS);
-    // tuning knob: L2 fetch granularity in bytes (32/64/128); random 16-32 B slot accesses want the smallest
-    if (cfg->reserved[1]) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)cfg->reserved[1]);
+    if (cfg->reserved[1]) c->min_capacity = std::max<u64>(8192, cfg->reserved[1]);
+    c->test_start_small = (cfg->reserved[2] >> 8) & 1;  // test hook: start at min_capacity, no pilot -> exercises deferral + growth
+    c->fixed_regions = (u32)std::min<u64>(cfg->reserved[3], SP_MAX_BUCKETS);
     auto bail = [&](int code) { g_create_error = c->err; gx_destroy(c); return code; };
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(c, GX_ERR_CUDA, "stream"));
     c->own_stream = true;
-    cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
-    cudaEventCreateWithFlags(&c->aux_event, cudaEventDisableTiming);
     if (cudaMalloc((void**)&c->d_ctr, sizeof(Counters)) != cudaSuccess) return bail(fail(c, GX_ERR_NOMEM, "counters"));
     if (cudaMallocHost((void**)&c->h_ctr, sizeof(Counters)) != cudaSuccess) return bail(fail(c, GX_ERR_NOMEM, "pinned counters"));
     if (c->ops->prepare() != 0) return bail(fail(c, GX_ERR_CUDA, "cudaFuncSetAttribute failed"));
-    c->spill_cap = 4ull << 20;
+    c->spill_cap = 1ull << 20;
     for (int i = 0; i < 2; ++i) {
         if (ensure(c, c->spill_keys[i], (size_t)c->spill_cap * c->kw * sizeof(u64)) != GX_OK ||
-            ensure(c, c->spill_meta[i], (size_t)c->spill_cap * sizeof(unsigned short)) != GX_OK)
+            ensure(c, c->spill_meta[i], (size_t)c->spill_cap * sizeof(unsigned short)) != GX_OK ||
+            ensure(c, c->spill_counts[i], (size_t)c->spill_cap * sizeof(u32)) != GX_OK)
             return bail(GX_ERR_NOMEM);
     }
     int r = gx_reset(c);
@@ -691,8 +664,8 @@ int gx_reset(gx_ctx* c) {
     CUDA_TRY(c, cudaMemcpyAsync(c->d_ctr, c->h_ctr, sizeof z, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     c->table_live = false;  // keep the allocation; it is re-initialised on first use
-    c->new_key_ratio = -1.0;
-    c->ratio_distinct0 = c->ratio_pending_occ = 0;
+    c->keys_estimated = false;
+    c->upserted_records = 0;
     c->spill_cur = 0;
     GX_TRY(set_spill_target(c));
     GX_TRY(mg_reset(c));
@@ -718,14 +691,13 @@ void gx_destroy(gx_ctx* c) {
     for (auto e : c->event_pool) cudaEventDestroy(e);
     DevBuf* bufs[] = {&c->heads, &c->store, &c->text, &c->nl_pos, &c->nl_pos2, &c->desc, &c->tile_sums, &c->hslot, &c->hcount, &c->hstart,
                       &c->hperm, &c->tile_bytes, &c->tile_nodes, &c->records, &c->rec_offsets, &c->parts, &c->dense,
-                      &c->flat_keys, &c->flat_meta, &c->part_keys, &c->part_meta, &c->bucket_count, &c->gstats};
+                      &c->tile_prefix, &c->deferred[0], &c->deferred[1], &c->gstats};
     for (auto* b : bufs) release(*b);
-    for (int i = 0; i < 2; ++i) { release(c->spill_keys[i]); release(c->spill_meta[i]); }
+    release_arena(c->arena);
+    for (int i = 0; i < 2; ++i) { release(c->spill_keys[i]); release(c->spill_meta[i]); release(c->spill_counts[i]); }
     if (c->table) cudaFree(c->table);
     if (c->d_ctr) cudaFree(c->d_ctr);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
-    if (c->aux_stream) { cudaStreamSynchronize(c->aux_stream); cudaStreamDestroy(c->aux_stream); }
-    if (c->aux_event) cudaEventDestroy(c->aux_event);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -839,7 +811,7 @@ int gx_finish(gx_ctx* c) {
         if (pending) return fail(c, GX_ERR_STATE, "gx_finish: %llu routed records not exchanged yet (call gx_mg_exchange on every rank first)",
                                  (unsigned long long)pending);
     }
-    if (!c->table || !c->table_live) { u64 room; GX_TRY(reserve_room(c, 0, 0, 0, &room)); }  // empty job: empty table, zero records
+    if (!c->table || !c->table_live) GX_TRY(ensure_table(c, c->min_capacity));  // empty job: empty table, zero records
     const u64 cap = c->capacity;
     const u64 n_heads = c->h_ctr->head_cursor;
     const u64 n_tiles = (cap + EM_TILE - 1) / EM_TILE;
@@ -855,7 +827,8 @@ int gx_finish(gx_ctx* c) {
             GX_TRY(ensure(c, c->tile_sums, (s_tiles + 1) * sizeof(u64)));
             CUDA_TRY(c, cudaMemsetAsync(c->hcount.p, 0, cap * sizeof(u32), c->stream));
             CUDA_TRY(c, cudaMemsetAsync(c->hperm.p, 0xff, n_heads * sizeof(u32), c->stream));
-            c->ops->heads_count(c->heads.p, n_heads, c->table, cap, (u64*)c->hslot.p, (u32*)c->hcount.p, c->d_ctr, c->stream);
+            c->ops->heads_count(c->heads.p, n_heads, c->table, cap, (u32)c->cfg.n_ranks, (u64*)c->hslot.p, (u32*)c->hcount.p, c->d_ctr,
+                                c->stream);
             GX_TRY(check_launch(c, "heads_count"));
             tile_sum_u32_kernel<<<(unsigned)s_tiles, TS_THREADS, 0, c->stream>>>((const u32*)c->hcount.p, cap, (u64*)c->tile_sums.p);
             GX_TRY(check_launch(c, "tile_sum_u32"));

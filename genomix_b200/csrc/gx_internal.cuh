@@ -72,12 +72,23 @@ __host__ __device__ __forceinline__ u64 hash_key(const u64 (&w)[KW]) {
     return h;
 }
 
-// owner rank of a key: independent of the slot bits (uses a re-mix)
-__host__ __device__ __forceinline__ u32 owner_of(u64 h, u32 n_ranks) {
-    return (u32)(((mix64(h ^ 0xd6e8feb86659fd93ull) >> 32) * (u64)n_ranks) >> 32);
+// One 64-bit hash h of the key drives every placement decision, most significant bits first:
+//   owner rank   = floor(h * n_ranks / 2^64)                     (which GPU's table holds the key)
+//   local hash   = h * n_ranks mod 2^64                          (uniform again inside the owner's range)
+//   table region = floor(local * n_regions / 2^64)               (bucket of the region-sorted build, gx_split.cuh)
+//   home slot    = floor(local * capacity / 2^64)
+// so regions are contiguous slot ranges and one multisplit pass serves both the exchange and the L2-blocked insert.
+__host__ __device__ __forceinline__ u64 mulhi64(u64 a, u64 b) {
+#ifdef __CUDA_ARCH__
+    return __umul64hi(a, b);
+#else
+    return (u64)(((unsigned __int128)a * b) >> 64);
+#endif
 }
-
-__device__ __forceinline__ u64 slot_of(u64 h, u64 capacity) { return __umul64hi(h, capacity); }
+__host__ __device__ __forceinline__ u32 owner_of(u64 h, u32 n_ranks) { return (u32)mulhi64(h, (u64)n_ranks); }
+__host__ __device__ __forceinline__ u64 local_hash(u64 h, u32 n_ranks) { return h * (u64)n_ranks; }
+__host__ __device__ __forceinline__ u32 region_of(u64 hl, u32 n_regions) { return (u32)mulhi64(hl, (u64)n_regions); }
+__host__ __device__ __forceinline__ u64 slot_of(u64 hl, u64 capacity) { return mulhi64(hl, capacity); }
 
 // reverse the order of the 32 2-bit groups of x and complement them (A<->T, C<->G: 3 - code)
 __host__ __device__ __forceinline__ u64 revcomp_word(u64 x) {

@@ -9,35 +9,32 @@ constexpr int KW = GX_KW;
 void l_init_table(u64* table, u64 capacity, cudaStream_t st) {
     init_table_kernel<KW><<<grid_for(capacity * SlotTraits<KW>::WORDS, 256, 148 * 32), 256, 0, st>>>(table, capacity);
 }
-void l_extract_insert(const ExtractArgs& a, cudaStream_t st) {
-    extract_kernel<KW, EX_UPSERT><<<grid_for(a.n_lines, EX_WARPS, 148 * 8), EX_THREADS, 0, st>>>(a);
+void l_split_count(const SplitArgs& a, cudaStream_t st) {
+    split_count_kernel<KW><<<grid_for(a.n_lines, SP_WARPS, 148 * SplitBlocks<KW>::MIN), SP_THREADS, 0, st>>>(a);
 }
-void l_extract_route(const ExtractArgs& a, cudaStream_t st) {
-    extract_kernel<KW, EX_ROUTE><<<grid_for(a.n_lines, EX_WARPS, 148 * 8), EX_THREADS, 0, st>>>(a);
+void l_split_place(const SplitArgs& a, cudaStream_t st) {
+    // one resident wave: the multisplit's global reservations then walk every bucket front to back exactly once per CTA
+    split_place_kernel<KW><<<grid_for(a.n_lines, SP_WARPS, 148 * SplitBlocks<KW>::MIN), SP_THREADS, sizeof(SplitSmem<KW>), st>>>(a);
 }
-void l_extract_flat(const ExtractArgs& a, cudaStream_t st) {
-    extract_kernel<KW, EX_FLAT><<<grid_for(a.n_lines, EX_WARPS, 148 * 8), EX_THREADS, 0, st>>>(a);
+void l_upsert_regions(const UpsertArgs& a, unsigned grid, cudaStream_t st) {
+    upsert_regions_kernel<KW><<<grid, UP_THREADS, sizeof(UpsertSmem<KW>), st>>>(a);
 }
-void l_partition_flat(const u64* flat_keys, const unsigned short* flat_meta, u64 n, u32 n_buckets, u64* bucket_cursor,
-                      u64* out_keys, unsigned short* out_meta, cudaStream_t st) {
-    if (n == 0) return;
-    partition_flat_kernel<KW><<<(unsigned)((n + PT_THREADS * PT_ITEMS - 1) / (PT_THREADS * PT_ITEMS)), PT_THREADS, 0, st>>>(
-        flat_keys, flat_meta, n, n_buckets, bucket_cursor, out_keys, out_meta);
+void l_check_arena(const u64* keys, const u64* seg_start, u32 n_ranks, u32 n_regions, u64* bad, cudaStream_t st) {
+    check_arena_kernel<KW><<<148 * 8, 256, 0, st>>>(keys, seg_start, n_ranks, n_regions, bad);
 }
 void l_insert_records(const u64* keys, const unsigned short* meta, const u32* counts, u64 n, u64* table, u64 capacity,
-                      Counters* ctr, cudaStream_t st) {
+                      u32 n_ranks, Counters* ctr, cudaStream_t st) {
     if (n == 0) return;
-    // short-lived CTAs (4 records per thread) so that concurrent kernels of other streams (NCCL) get SM slots promptly
-    insert_records_kernel<KW><<<(unsigned)std::min<u64>((n + 1023) / 1024, 1u << 30), 256, 0, st>>>(keys, meta, counts, n, table, capacity, ctr);
+    insert_records_kernel<KW><<<grid_for(n, 256, 148 * 8), 256, 0, st>>>(keys, meta, counts, n, table, capacity, n_ranks, ctr);
 }
-void l_rehash(const u64* old_table, u64 old_capacity, u64* table, u64 capacity, cudaStream_t st) {
-    rehash_kernel<KW><<<grid_for(old_capacity, 256, 148 * 8), 256, 0, st>>>(old_table, old_capacity, table, capacity);
+void l_rehash(const u64* old_table, u64 old_capacity, u64* table, u64 capacity, u32 n_ranks, Counters* ctr, cudaStream_t st) {
+    rehash_kernel<KW><<<grid_for(old_capacity, 256, 148 * 8), 256, 0, st>>>(old_table, old_capacity, table, capacity, n_ranks, ctr);
 }
-void l_heads_count(const void* heads, u64 n_heads, const u64* table, u64 capacity, u64* hslot, u32* hcount,
+void l_heads_count(const void* heads, u64 n_heads, const u64* table, u64 capacity, u32 n_ranks, u64* hslot, u32* hcount,
                    Counters* ctr, cudaStream_t st) {
     if (n_heads == 0) return;
     heads_count_kernel<KW><<<(unsigned)((n_heads + 255) / 256), 256, 0, st>>>(
-        reinterpret_cast<const Head<KW>*>(heads), n_heads, table, capacity, hslot, hcount, ctr);
+        reinterpret_cast<const Head<KW>*>(heads), n_heads, table, capacity, n_ranks, hslot, hcount, ctr);
 }
 void l_heads_sort(const void* heads, const u64* hslot, u64 n_heads, u64 capacity, const u32* hstart, u32* hcount,
                   u32* hperm, Counters* ctr, cudaStream_t st) {
@@ -68,17 +65,22 @@ void l_rebase_heads(void* heads, u64 first, u64 n, u64 store_base, cudaStream_t 
     rebase_heads_kernel<KW><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(heads, first, n, store_base);
 }
 int l_prepare() {
-    return (int)cudaFuncSetAttribute(emit_serialise_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, EM_MAX_STAGE_BYTES);
+    int r = (int)cudaFuncSetAttribute(emit_serialise_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, EM_MAX_STAGE_BYTES);
+    if (r == 0)
+        r = (int)cudaFuncSetAttribute(split_place_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem<KW>));
+    if (r == 0)
+        r = (int)cudaFuncSetAttribute(upsert_regions_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpsertSmem<KW>));
+    return r;
 }
 
 const EngineOps OPS = {KW,
                        sizeof(u64) * SlotTraits<KW>::WORDS,
                        sizeof(Head<KW>),
                        l_init_table,
-                       l_extract_insert,
-                       l_extract_route,
-                       l_extract_flat,
-                       l_partition_flat,
+                       l_split_count,
+                       l_split_place,
+                       l_upsert_regions,
+                       l_check_arena,
                        l_insert_records,
                        l_rehash,
                        l_heads_count,

@@ -32,6 +32,8 @@ struct Counters {
     u64 spill_cap;
     u64* spill_keys;
     unsigned short* spill_meta;
+    u32* spill_counts;   // occurrence count carried by each spilled record
+    u64 deferred_count;  // work items of the region upsert postponed because the table reached its load limit
     u64 scratch[2];
 };
 

@@ -1,0 +1,585 @@
+// gx_split.cuh -- the build: region-sorted k-mer records, L2-resident upserts.
+//
+// Replaces the reference's sort + pre-clustered group (ExternalSortOperatorDescriptor.java:119-194,
+// PreclusteredGroupWriter.java:76-136) with ONE radix pass on the top bits of the key hash instead of a comparison sort,
+// and the sender side of its M:N hash connector (MToNPartitioningMergingConnectorDescriptor.java:65-87) with the same pass:
+//
+//   split_count_kernel<KW>    read -> canonical k-mers -> histogram over buckets (owner GPU, table region). Exact record
+//                             counts per bucket, so that the placement pass writes a dense, gap-free record arena.
+//   split_place_kernel<KW>    read -> canonical k-mers + edge masks + read heads -> CTA-level multisplit in shared memory
+//                             -> bucket-sorted runs appended to the arena (or, for buckets owned by another GPU, straight
+//                             into that GPU's inbox over NVLink). No table access: a pure function of the text.
+//   upsert_regions_kernel<KW> persistent kernel that walks the arenas region by region, so that at any time all CTAs
+//                             upsert into the same few MB of the table (L2 hits instead of one HBM row activation per
+//                             k-mer occurrence), prefetching the next region into L2 as it goes.
+//
+// A random 16-byte table access that misses L2 costs a whole 128-byte line and a DRAM row activation (15.6 G upserts/s on
+// B200, profiles/r01_microbench_random_access.txt); the same access L2-resident runs 4x faster. Sorting the records by
+// region first costs one coalesced write + read of (8*KW + 2) bytes per occurrence plus a second extraction pass.
+#pragma once
+#include "gx_build.cuh"
+
+namespace gx {
+
+static constexpr int SP_THREADS = 512;
+static constexpr int SP_WARPS = SP_THREADS / 32;
+static constexpr int SP_NPL = 4;                // consecutive positions per lane and round
+static constexpr int SP_MAX_BUCKETS = 1024;     // owners x regions handled by one multisplit
+static constexpr int SP_MAX_RANKS = 64;
+static constexpr int CURSOR_PAD = 16;           // bucket cursors live 128 B apart (one L2 line each)
+
+struct SplitArgs {
+    const uint8_t* text; u64 n_text;
+    const LineDesc* desc; u64 n_lines;
+    int k;
+    void* heads;
+    uint8_t* store;
+    Counters* ctr;
+    u32 n_ranks;            // owner = owner_of(h, n_ranks)
+    u32 n_regions;          // table regions per owner; bucket = owner * n_regions + region_of(local hash)
+    u64* bucket_count;      // count pass: [n_buckets] records per bucket
+    u64* cursor;            // place pass: [n_buckets * CURSOR_PAD] next record index of each bucket inside its owner's area
+    u64* owner_keys[SP_MAX_RANKS];             // record area of each owner (KW words per record): the local arena or,
+    unsigned short* owner_meta[SP_MAX_RANKS];  // with direct NVLink delivery, this rank's share of the owner's inbox
+};
+
+template <int KW> struct SplitBlocks { static constexpr int MIN = (KW == 1) ? 2 : 1; };
+
+template <int KW>
+struct SplitSmem {
+    static constexpr int T = SP_THREADS * SP_NPL;  // records per CTA round (upper bound)
+    u64 win[SP_WARPS][WIN_WORDS];
+    u64 keys[T * KW];
+    u64 gbase[SP_MAX_BUCKETS];   // record index (in the owner's area) that stage position start[b] goes to
+    u32 cnt[SP_MAX_BUCKETS];     // records of this round per bucket (zero between rounds)
+    u32 start[SP_MAX_BUCKETS];   // first stage position of the bucket's run
+    unsigned short meta[T];
+    unsigned short bkt[T];
+    u32 warp_sums[SP_WARPS];
+};
+
+// A warp's walk over the split mates of its lines: line = line0 + i * stride, mate 0 then mate 1.
+struct ReadCursor {
+    u64 line0, stride, cand;    // next candidate: line0 + (cand >> 1) * stride, mate cand & 1
+    u64 cur_line;
+    u32 flags, len[2], off[2];  // hot fields of the current line's descriptor
+};
+
+// (Re)load the packed 2-bit window of the read so that letters [need_lo, need_hi) are present. Warp-uniform.
+__device__ __forceinline__ void ensure_window(u64* W, const uint8_t* rd, u32 len, u32 need_lo, u32 need_hi, u32& win_lo, u32& win_hi,
+                                              u32& win_m, const uint8_t* text_lo, const uint8_t* text_hi, int lane) {
+    constexpr u32 WIN_LETTERS = 4u * WIN_BYTES - 4u;   // letters a window can hold whatever the source alignment
+    if (need_lo >= win_lo && need_hi <= win_hi) return;
+    uint8_t* Wb = reinterpret_cast<uint8_t*>(W);
+    win_lo = need_lo;
+    win_hi = min(len, win_lo + WIN_LETTERS);
+    const uint8_t* src = rd + win_lo;
+    win_m = (u32)((uintptr_t)src & 3u);
+    const uint8_t* aligned = src - win_m;
+    const u32 nwords = (win_m + (win_hi - win_lo) + 3u) / 4u;
+    __syncwarp();
+    for (u32 j = lane; j < nwords; j += 32) Wb[j] = (uint8_t)load_quad(aligned + 4 * j, text_lo, text_hi);
+    __syncwarp();
+}
+
+// Canonical keys of positions q .. q+NPL-1 (those below pend) from the packed window: key = min(fwd, rc), bit j of
+// revbits set when position q+j is REVERSE (ReadsKeyValueParserFactory.java:163,181: ties are FORWARD).
+template <int KW>
+__device__ __forceinline__ void lane_keys(const u64* W, u32 wbase, u32 q, u32 pend, int k, u64 (&key)[SP_NPL][KW], u32& revbits) {
+    u64 f[KW], rc[KW];
+    revbits = 0;
+    if (q < pend) {
+        window_kmer<KW>(W, q + wbase, k, f);
+        revcomp_key<KW>(f, k, rc);
+    }
+#pragma unroll
+    for (int j = 0; j < SP_NPL; ++j) {
+        if (q + j < pend) {
+            const bool rev = !key_le<KW>(f, rc);
+            revbits |= (u32)rev << j;
+#pragma unroll
+            for (int i = 0; i < KW; ++i) key[j][i] = rev ? rc[i] : f[i];
+            if (j + 1 < SP_NPL && q + j + 1 < pend) roll_kmer<KW>(f, rc, k, window_letter(W, q + j + (u32)k + wbase));
+        }
+    }
+}
+
+__device__ __forceinline__ u32 bucket_of_hash(u64 h, u32 n_ranks, u32 n_regions) {
+    return owner_of(h, n_ranks) * n_regions + region_of(local_hash(h, n_ranks), n_regions);
+}
+
+// K1a. Histogram of the chunk's k-mer occurrences over buckets. Same extraction as the placement pass, no output but the
+// counts: warps run independently (no CTA rounds), the CTA's histogram is flushed once at the end.
+template <int KW>
+__global__ void __launch_bounds__(SP_THREADS, SplitBlocks<KW>::MIN) split_count_kernel(SplitArgs a) {
+    __shared__ u64 win[SP_WARPS][WIN_WORDS];
+    __shared__ u32 hist[SP_MAX_BUCKETS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (u32 b = tid; b < SP_MAX_BUCKETS; b += SP_THREADS) hist[b] = 0;
+    __syncthreads();
+    u64* W = win[warp];
+    const int k = a.k;
+    const uint8_t* text_lo = a.text;
+    const uint8_t* text_hi = a.text + a.n_text;
+    constexpr u32 CHUNK = 32u * SP_NPL;
+    for (u64 line = (u64)blockIdx.x * SP_WARPS + warp; line < a.n_lines; line += (u64)gridDim.x * SP_WARPS) {
+        const LineDesc& dd = a.desc[line];
+        const u32 flags = dd.flags;
+        if ((flags & 3u) == 0) continue;
+#pragma unroll 1
+        for (int mate = 0; mate < 2; ++mate) {
+            if (!(flags & (1u << mate))) continue;
+            const u32 len = dd.len[mate];
+            const uint8_t* rd = a.text + dd.off[mate];
+            const u32 npos = len - (u32)k + 1u;
+            u32 win_lo = 0, win_hi = 0, win_m = 0;
+            for (u32 p0 = 0; p0 < npos; p0 += CHUNK) {
+                const u32 pend = min(p0 + CHUNK, npos);
+                ensure_window(W, rd, len, p0, min(pend + (u32)k, len), win_lo, win_hi, win_m, text_lo, text_hi, lane);
+                const u32 wbase = win_m - win_lo;
+                const u32 q = p0 + (u32)SP_NPL * (u32)lane;
+                u64 key[SP_NPL][KW];
+                u32 revbits;
+                lane_keys<KW>(W, wbase, q, pend, k, key, revbits);
+#pragma unroll
+                for (int j = 0; j < SP_NPL; ++j)
+                    if (q + j < pend) atomicAdd(&hist[bucket_of_hash(hash_key<KW>(key[j]), a.n_ranks, a.n_regions)], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    const u32 nb = a.n_ranks * a.n_regions;
+    for (u32 b = tid; b < nb; b += SP_THREADS)
+        if (hist[b]) atomicAdd(a.bucket_count + b, (u64)hist[b]);
+}
+
+// Exclusive prefix of the bucket counts -> seg_start[n_buckets + 1] (record index of each bucket's first record in the
+// arena, owner-major, so every owner's records are one contiguous block) and the placement cursors. With `relative`
+// the cursors count from the start of the owner's block (direct delivery into per-owner areas), else from the arena.
+static __global__ void __launch_bounds__(1024) split_prefix_kernel(const u64* __restrict__ bucket_count, u32 n_buckets, u32 n_regions,
+                                                            int relative, u64* __restrict__ seg_start, u64* __restrict__ cursor) {
+    __shared__ u64 sh_start[SP_MAX_BUCKETS + 1];
+    const u32 b = threadIdx.x;
+    const u64 v = b < n_buckets ? bucket_count[b] : 0ull;
+    u64 tot;
+    const u64 ex = block_scan_excl<1024>(v, &tot);
+    if (b < n_buckets) sh_start[b] = ex;
+    if (b == 0) { sh_start[n_buckets] = tot; seg_start[n_buckets] = tot; }
+    __syncthreads();
+    if (b < n_buckets) seg_start[b] = sh_start[b];
+    if (b < n_buckets) cursor[(size_t)b * CURSOR_PAD] = relative ? sh_start[b] - sh_start[(b / n_regions) * n_regions] : sh_start[b];
+}
+
+// K1b. Restates ReadsKeyValueParserFactory.SplitReads (:150-196) and setEdgesForCurAndNext (:209-233): for every position p
+// of every split mate the forward and reverse-complement k-mers, dir = fwd <= rc ? FORWARD : REVERSE, key = the smaller, one
+// tuple (key, Node{coverage 1, <=2 edges, read head on p == 0}). The tuples leave the kernel as (key, 16-bit edge mask)
+// records sorted by bucket; read heads go to the heads array, packed reads to the read store.
+// A warp owns one read at a time and handles 32*NPL consecutive positions per CTA round: lane l computes the k-mer at
+// position p0 + NPL*l from the packed window and rolls it forward NPL-1 times; the directions of the neighbouring
+// positions come from the adjacent lanes (shuffles). The last position of a full chunk is a halo (computed for its
+// direction, emitted by the next chunk).
+template <int KW>
+__global__ void __launch_bounds__(SP_THREADS, SplitBlocks<KW>::MIN) split_place_kernel(SplitArgs a) {
+    constexpr int NPL = SP_NPL;
+    extern __shared__ __align__(16) unsigned char split_smem_raw[];
+    SplitSmem<KW>& S = *reinterpret_cast<SplitSmem<KW>*>(split_smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (u32 b = tid; b < SP_MAX_BUCKETS; b += SP_THREADS) S.cnt[b] = 0;
+    u64* W = S.win[warp];
+    Head<KW>* heads = reinterpret_cast<Head<KW>*>(a.heads);
+    const int k = a.k;
+    const uint8_t* text_lo = a.text;
+    const uint8_t* text_hi = a.text + a.n_text;
+    constexpr u32 CHUNK = 32u * NPL;
+
+    // this warp's walk over (line, mate) candidates
+    const u64 line0 = (u64)blockIdx.x * SP_WARPS + warp;
+    const u64 line_stride = (u64)gridDim.x * SP_WARPS;
+    u64 cand = 0;               // next candidate: line0 + (cand >> 1) * line_stride, mate cand & 1
+    bool in_read = false;
+    u64 cur_line = 0;           // only the hot fields of the line descriptor stay in registers
+    u32 d_flags = 0, d_len[2] = {0, 0}, d_off[2] = {0, 0};
+    int mate = 0;
+    u32 len = 0, npos = 0, p0 = 0, win_lo = 0, win_hi = 0, win_m = 0, carry_rev = 0;
+    const uint8_t* rd = nullptr;
+
+    for (;;) {
+        // ---- 1. a read with positions left
+        while (!in_read) {
+            const u64 ln = line0 + (cand >> 1) * line_stride;
+            if (ln >= a.n_lines) break;
+            const int mt = (int)(cand & 1);
+            ++cand;
+            if (mt == 0) {
+                const LineDesc& dd = a.desc[ln];
+                cur_line = ln;
+                d_flags = dd.flags; d_len[0] = dd.len[0]; d_len[1] = dd.len[1]; d_off[0] = dd.off[0]; d_off[1] = dd.off[1];
+                if ((d_flags & 3u) == 0) { ++cand; continue; }   // nothing of this line is split: skip both mates
+            }
+            const u32 l = mt ? d_len[1] : d_len[0];
+            if (l == 0) continue;
+            const uint8_t* letters = a.text + (mt ? d_off[1] : d_off[0]);
+            pack_read_to_store(letters, l, a.store + a.desc[ln].store[mt], lane);
+            if (!(d_flags & (1u << mt))) continue;
+            mate = mt; len = l; npos = l - (u32)k + 1u; p0 = 0; rd = letters;
+            win_lo = win_hi = 0; carry_rev = 0;
+            in_read = true;
+        }
+        if (!__syncthreads_or(in_read ? 1 : 0)) break;   // also separates the rounds' use of the stage
+
+        // ---- 2. this warp's chunk: positions [p0, pend) computed, [p0, pemit) emitted
+        u64 key[NPL][KW];
+        u32 msk[NPL];
+        u32 emit = 0;   // bit j: record j of this lane is emitted
+        if (in_read) {
+            const u32 pend = min(p0 + CHUNK, npos);
+            const u32 pemit = (p0 + CHUNK < npos) ? p0 + CHUNK - 1u : npos;
+            ensure_window(W, rd, len, p0 > 0 ? p0 - 1u : 0u, min(pend + (u32)k, len), win_lo, win_hi, win_m, text_lo, text_hi, lane);
+            const u32 wbase = win_m - win_lo;   // letter x sits at packed index x + wbase (mod 2^32)
+            const u32 q = p0 + (u32)NPL * (u32)lane;
+            u32 revbits;
+            lane_keys<KW>(W, wbase, q, pend, k, key, revbits);
+            u32 prev_first = __shfl_up_sync(0xffffffffu, (revbits >> (NPL - 1)) & 1u, 1);
+            if (lane == 0) prev_first = carry_rev;
+            const u32 next_last = __shfl_down_sync(0xffffffffu, revbits & 1u, 1);
+#pragma unroll
+            for (int j = 0; j < NPL; ++j) {
+                const u32 p = q + j;
+                msk[j] = 0;
+                if (p < pemit) {
+                    emit |= 1u << j;
+                    const bool rev = (revbits >> j) & 1u;
+                    const u32 prev_rev = j ? (revbits >> (j - 1)) & 1u : prev_first;
+                    const u32 next_rev = (j + 1 < NPL) ? (revbits >> (j + 1)) & 1u : next_last;
+                    u32 m = 0;
+                    if (p + 1u < npos) m |= edge_bit_next(rev, next_rev, window_letter(W, p + (u32)k + wbase));
+                    if (p > 0u) m |= edge_bit_prev(rev, prev_rev, window_letter(W, p - 1u + wbase));
+                    msk[j] = m;
+                    if (p == 0u) write_head<KW>(heads, a.desc[cur_line], mate, key[j], rev, k);
+                }
+            }
+            // direction of position pemit - 1 for the next chunk (only meaningful after a full chunk)
+            carry_rev = __shfl_sync(0xffffffffu, (revbits >> (NPL - 2)) & 1u, 31);
+            p0 = pemit;
+            if (p0 >= npos) in_read = false;
+        }
+
+        // ---- 3. multisplit of the round's records by bucket
+        u32 bk[NPL], rk[NPL];
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            if ((emit >> j) & 1u) {
+                bk[j] = bucket_of_hash(hash_key<KW>(key[j]), a.n_ranks, a.n_regions);
+                rk[j] = atomicAdd(&S.cnt[bk[j]], 1u);
+            }
+        }
+        __syncthreads();
+        // exclusive scan over the buckets (two per thread) and ONE global reservation per non-empty bucket
+        static_assert(SP_MAX_BUCKETS == 2 * SP_THREADS, "two buckets per thread");
+        const u32 b0 = 2u * tid, b1 = b0 + 1u;
+        const u32 c0 = S.cnt[b0], c1 = S.cnt[b1];
+        u32 incl = c0 + c1;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) S.warp_sums[warp] = incl;
+        __syncthreads();
+        u32 wsum = lane < SP_WARPS ? S.warp_sums[lane] : 0u;   // every warp scans the 16 warp sums itself
+#pragma unroll
+        for (int d = 1; d < SP_WARPS; d <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, wsum, d);
+            if (lane >= d) wsum += t;
+        }
+        const u32 total = __shfl_sync(0xffffffffu, wsum, SP_WARPS - 1);
+        const u32 wex = warp ? __shfl_sync(0xffffffffu, wsum, warp - 1) : 0u;
+        const u32 ex = wex + incl - (c0 + c1);
+        if (c0) {   // b < n_buckets because only such buckets were counted
+            S.start[b0] = ex;
+            S.gbase[b0] = atomicAdd(a.cursor + (size_t)b0 * CURSOR_PAD, (u64)c0);
+            S.cnt[b0] = 0;
+        }
+        if (c1) {
+            S.start[b1] = ex + c0;
+            S.gbase[b1] = atomicAdd(a.cursor + (size_t)b1 * CURSOR_PAD, (u64)c1);
+            S.cnt[b1] = 0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            if ((emit >> j) & 1u) {
+                const u32 pos = S.start[bk[j]] + rk[j];
+#pragma unroll
+                for (int i = 0; i < KW; ++i) S.keys[pos * KW + i] = key[j][i];
+                S.meta[pos] = (unsigned short)msk[j];
+                S.bkt[pos] = (unsigned short)bk[j];
+            }
+        }
+        __syncthreads();
+        // copy-out: consecutive stage positions of a bucket go to consecutive records of its owner's area
+        for (u32 i = tid; i < total; i += SP_THREADS) {
+            const u32 b = S.bkt[i];
+            const u64 g = S.gbase[b] + (i - S.start[b]);
+            const u32 o = a.n_ranks > 1 ? b / a.n_regions : 0u;
+            u64* kd = a.owner_keys[o] + g * KW;
+            if constexpr (KW == 2) {
+                *reinterpret_cast<ulonglong2*>(kd) = *reinterpret_cast<const ulonglong2*>(&S.keys[i * 2]);
+            } else {
+#pragma unroll
+                for (int w = 0; w < KW; ++w) kd[w] = S.keys[i * KW + w];
+            }
+            a.owner_meta[o][g] = S.meta[i];
+        }
+    }
+}
+
+// Debug aid (GENOMIX_GB_DEBUG=1): number of arena records that do not sit in the bucket their hash names.
+template <int KW>
+__global__ void __launch_bounds__(256) check_arena_kernel(const u64* __restrict__ keys, const u64* __restrict__ seg_start, u32 n_ranks,
+                                                          u32 n_regions, u64* __restrict__ bad) {
+    const u32 n_buckets = n_ranks * n_regions;
+    const u64 n = seg_start[n_buckets];
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        u64 key[KW];
+#pragma unroll
+        for (int j = 0; j < KW; ++j) key[j] = keys[i * KW + j];
+        const u32 b = bucket_of_hash(hash_key<KW>(key), n_ranks, n_regions);
+        if (i < seg_start[b] || i >= seg_start[b + 1]) atomicAdd(bad, 1ull);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2. Region-by-region upsert of bucket-sorted record areas.
+//
+// Work item = UP_ITEM consecutive records of one (region, source) pair, handled by ONE warp on its own (no CTA barriers:
+// the 16-32 warps of an SM sit in different stages, which is what hides the L2 latency). Items are dealt round-robin, so
+// at any time all warps of the GPU work inside the same region or two of the table. Per item:
+//   stage 1  every lane loads its 4 records and their 4 home slots (all loads in flight together);
+//   stage 2  from the slot snapshots: key present -> fold (fire-and-forget RED), slot empty -> claim it (CAS; all of a
+//            lane's claims in flight together), slot taken by another key -> slow queue;
+//   stage 3  claims that succeeded get their value folded in, claims lost to another key -> slow queue;
+//   slow     the few queued records (about 6 % at load 0.4) are compacted into the low lanes and walk their probe
+//            sequences with the general table_upsert. Without the queue every warp would wait for the longest probe
+//            sequence among its 32 lanes, four times per item (measured: 3.7 dependent L2 round trips per record).
+static constexpr int UP_THREADS = 512;
+static constexpr int UP_WARPS = UP_THREADS / 32;
+static constexpr int UP_PER_LANE = 4;
+static constexpr int UP_ITEM = 32 * UP_PER_LANE;             // records per work item
+static constexpr int UP_PUBLISH = 512;                       // a warp publishes its new-key count at the latest after this many
+static constexpr int UP_MAX_SRC = 64;                        // record areas walked by one launch (own + received from peers)
+
+struct UpsertSrc {
+    const u64* keys; const unsigned short* meta;   // the owner's record area (block start)
+    const u64* seg;        // [n_regions + 1] record index of each region's first record; region r holds seg[r+1] - seg[r]
+    u64 rebase;            // 1: indices in seg count from seg[0] (a block cut out of a larger arena), 0: from the area start
+};
+
+struct UpsertArgs {
+    UpsertSrc src[UP_MAX_SRC];
+    u32 n_src;
+    u32 r0, r1;            // regions [r0, r1) of this launch, walked in order; pair index i = (region - r0) * n_src + src
+    u32 n_regions;
+    u32 n_ranks;
+    u32 active_warps;      // warps per CTA that take work (fewer for tiny tables, so that the in-flight margin stays small)
+    u64* table; u64 capacity;
+    Counters* ctr;
+    const u32* item_prefix;    // [(r1 - r0) * n_src + 1] exclusive prefix of work items per pair
+    u64 hard_limit;            // work items are deferred (not applied) once ctr->distinct exceeds this
+    u32* deferred_out;         // deferred work item ids -> ctr->deferred_count
+    const u32* deferred_in;    // != nullptr: apply exactly these n_deferred_in work items
+    u32 n_deferred_in;
+};
+
+// exclusive prefix of work items per (region, source) pair; one CTA
+static __global__ void __launch_bounds__(1024) upsert_prefix_kernel(UpsertArgs a, u32* __restrict__ item_prefix) {
+    __shared__ u64 carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const u32 n_pairs = (a.r1 - a.r0) * a.n_src;
+    for (u32 base = 0; base < n_pairs; base += 1024) {
+        const u32 i = base + threadIdx.x;
+        u64 items = 0;
+        if (i < n_pairs) {
+            const u32 region = a.r0 + i / a.n_src, s = i % a.n_src;
+            items = (a.src[s].seg[region + 1] - a.src[s].seg[region] + UP_ITEM - 1) / UP_ITEM;
+        }
+        u64 tot;
+        const u64 ex = block_scan_excl<1024>(items, &tot);
+        const u64 carry = carry_s;
+        if (i < n_pairs) item_prefix[i] = (u32)(carry + ex);
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) item_prefix[n_pairs] = (u32)carry_s;
+}
+
+template <int KW> struct UpsertBlocks { static constexpr int MIN = (KW == 1) ? 2 : 1; };
+
+template <int KW>
+struct UpsertSmem {
+    u64 qkeys[UP_WARPS][UP_ITEM * KW];       // per-warp slow queue
+    unsigned short qmeta[UP_WARPS][UP_ITEM];
+};
+
+template <int KW>
+__global__ void __launch_bounds__(UP_THREADS, UpsertBlocks<KW>::MIN) upsert_regions_kernel(UpsertArgs a) {
+    constexpr int SW = SlotTraits<KW>::WORDS;
+    extern __shared__ __align__(16) unsigned char upsert_smem_raw[];
+    UpsertSmem<KW>& Q = *reinterpret_cast<UpsertSmem<KW>*>(upsert_smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if ((u32)warp >= a.active_warps) return;
+    const u32 lane_lt = (1u << lane) - 1u;
+    u64* qk = Q.qkeys[warp];
+    unsigned short* qm = Q.qmeta[warp];
+    const u32 n_pairs = (a.r1 - a.r0) * a.n_src;
+    const u32 total = a.deferred_in ? a.n_deferred_in : a.item_prefix[n_pairs];
+    const u32 gw = blockIdx.x * a.active_warps + warp, n_gw = gridDim.x * a.active_warps;
+    u32 pair = 0;
+    u32 unpublished = 0;                                 // slots this warp created and has not added to ctr->distinct yet
+    u64 next_distinct = ld_relaxed(&a.ctr->distinct);    // refreshed one item ahead, so the load never stalls the warp
+    for (u32 w = gw; w < total; w += n_gw) {
+        u32 t = w;
+        if (a.deferred_in) {
+            t = a.deferred_in[w];
+            u32 lo = 0, hi = n_pairs - 1;   // largest pair with item_prefix[pair] <= t
+            while (lo < hi) {
+                const u32 mid = (lo + hi + 1) >> 1;
+                if (a.item_prefix[mid] <= t) lo = mid; else hi = mid - 1;
+            }
+            pair = lo;
+        }
+        while (t >= a.item_prefix[pair + 1]) ++pair;   // skips empty pairs
+        // apply the item only while the table has room for everything that all warps in flight could still add
+        // (hard_limit leaves that margin); otherwise hand it back to the host, which grows the table
+        const u64 distinct_now = next_distinct;
+        next_distinct = ld_relaxed(&a.ctr->distinct);
+        if (distinct_now > a.hard_limit) {
+            if (lane == 0) a.deferred_out[atomicAdd(&a.ctr->deferred_count, 1ull)] = t;
+            continue;
+        }
+        const u32 region = a.r0 + pair / a.n_src, s = pair % a.n_src;
+        const UpsertSrc& S = a.src[s];
+        const u64 seg_lo = S.seg[region], count = S.seg[region + 1] - seg_lo;
+        const u64 item_off = (u64)(t - a.item_prefix[pair]) * UP_ITEM;
+        const u64 first = seg_lo - (S.rebase ? S.seg[0] : 0ull) + item_off;
+        const u32 n = (u32)min((u64)UP_ITEM, count - item_off);
+        const u64* keys = S.keys + first * KW;
+        const unsigned short* meta = S.meta + first;
+
+        // ---- stage 1: records and home-slot snapshots
+        u64 key[UP_PER_LANE][KW];
+        u32 m[UP_PER_LANE];
+        u64* sp[UP_PER_LANE];
+        Probe<KW> pr[UP_PER_LANE];
+#pragma unroll
+        for (int i = 0; i < UP_PER_LANE; ++i) {
+            const u32 r = lane + 32u * i;
+            if (r < n) {
+#pragma unroll
+                for (int j = 0; j < KW; ++j) key[i][j] = __ldcs(keys + (u64)r * KW + j);   // streamed once: evict first
+                m[i] = __ldcs(meta + r);
+                sp[i] = a.table + slot_of(local_hash(hash_key<KW>(key[i]), a.n_ranks), a.capacity) * SW;
+                probe_load<KW>(sp[i], pr[i]);
+            }
+        }
+        // ---- stage 2: fold what is there, claim what is empty
+        u32 slow = 0, claim = 0, n_new = 0;   // bit i: record i of this lane
+        u64 old0[UP_PER_LANE], old1[UP_PER_LANE];
+        if constexpr (KW <= 2) {
+#pragma unroll
+            for (int i = 0; i < UP_PER_LANE; ++i) {
+                if (lane + 32u * i >= n) continue;
+                bool eq = true, empty = true;
+#pragma unroll
+                for (int j = 0; j < KW; ++j) { eq = eq && pr[i].w[j] == key[i][j]; empty = empty && pr[i].w[j] == EMPTY_WORD; }
+                if (eq) fold_value(sp[i] + KW, 1ull, m[i], pr[i].w[KW]);
+                else if (empty) {
+                    claim |= 1u << i;
+                    if constexpr (KW == 1) { old0[i] = atomicCAS(sp[i], EMPTY_WORD, key[i][0]); old1[i] = 0; }
+                    else (void)cas128(sp[i], EMPTY_WORD, EMPTY_WORD, key[i][0], key[i][1], old0[i], old1[i]);
+                } else slow |= 1u << i;
+            }
+            // ---- stage 3: outcome of the claims
+#pragma unroll
+            for (int i = 0; i < UP_PER_LANE; ++i) {
+                if (!((claim >> i) & 1u)) continue;
+                const bool won = old0[i] == EMPTY_WORD && (KW == 1 || old1[i] == EMPTY_WORD);
+                const bool same = old0[i] == key[i][0] && (KW == 1 || old1[i] == key[i][KW - 1]);   // lost to the same key
+                if (won || same) { fold_value(sp[i] + KW, 1ull, m[i], 0ull); n_new += won ? 1u : 0u; }
+                else slow |= 1u << i;
+            }
+        } else {
+            // claim protocol: val 0 -> LOCK, write key words, publish val with release order
+            u64 kw0[UP_PER_LANE][KW];
+#pragma unroll
+            for (int i = 0; i < UP_PER_LANE; ++i) {
+                if (lane + 32u * i >= n) continue;
+                const u64 v = pr[i].w[0];
+                if (v == 0) { claim |= 1u << i; old0[i] = atomicCAS(sp[i] + KW, 0ull, VAL_LOCK); }
+                else if (v == VAL_LOCK) slow |= 1u << i;
+                else {
+#pragma unroll
+                    for (int j = 0; j < KW; ++j) kw0[i][j] = ld_relaxed(sp[i] + j);   // ordered after the acquire load of val
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < UP_PER_LANE; ++i) {
+                if (lane + 32u * i >= n || ((slow >> i) & 1u)) continue;
+                if ((claim >> i) & 1u) {
+                    if (old0[i] == 0ull) {
+#pragma unroll
+                        for (int j = 0; j < KW; ++j) st_relaxed(sp[i] + j, key[i][j]);
+                        st_release(sp[i] + KW, 1ull | ((u64)m[i] << MASK_SHIFT));
+                        ++n_new;
+                    } else slow |= 1u << i;   // somebody else is claiming this slot: look again on the slow path
+                } else {
+                    bool eq = true;
+#pragma unroll
+                    for (int j = 0; j < KW; ++j) eq = eq && kw0[i][j] == key[i][j];
+                    if (eq) fold_value(sp[i] + KW, 1ull, m[i], pr[i].w[0]);
+                    else slow |= 1u << i;
+                }
+            }
+        }
+        // ---- slow path: compact the leftovers into the low lanes, walk their probe sequences
+        if (__any_sync(0xffffffffu, slow != 0)) {
+            u32 qn = 0;
+#pragma unroll
+            for (int i = 0; i < UP_PER_LANE; ++i) {
+                const bool mine = (slow >> i) & 1u;
+                const u32 bal = __ballot_sync(0xffffffffu, mine);
+                if (mine) {
+                    const u32 pos = qn + __popc(bal & lane_lt);
+#pragma unroll
+                    for (int j = 0; j < KW; ++j) qk[pos * KW + j] = key[i][j];
+                    qm[pos] = (unsigned short)m[i];
+                }
+                qn += __popc(bal);
+            }
+            __syncwarp();
+            for (u32 j = lane; j < qn; j += 32) {
+                u64 k2[KW];
+#pragma unroll
+                for (int x = 0; x < KW; ++x) k2[x] = qk[j * KW + x];
+                const u32 m2 = qm[j];
+                bool is_new;
+                if (table_upsert<KW>(a.table, a.capacity, local_hash(hash_key<KW>(k2), a.n_ranks), k2, 1ull, m2, is_new) == a.capacity)
+                    spill_record<KW>(a.ctr, k2, m2);
+                n_new += is_new ? 1u : 0u;
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int dlt = 16; dlt > 0; dlt >>= 1) n_new += __shfl_xor_sync(0xffffffffu, n_new, dlt);
+        unpublished += n_new;
+        if (unpublished >= UP_PUBLISH) {
+            if (lane == 0) atomicAdd(&a.ctr->distinct, (u64)unpublished);
+            unpublished = 0;
+        }
+    }
+    if (lane == 0 && unpublished) atomicAdd(&a.ctr->distinct, (u64)unpublished);
+}
+
+}  // namespace gx

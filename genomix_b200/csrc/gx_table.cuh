@@ -70,31 +70,60 @@ __device__ __forceinline__ void fold_value(u64* val, u64 add, u32 mask, u64 seen
 // after growing the table. Never a hang, never a lost occurrence.
 static constexpr u64 PROBE_BUDGET = 1ull << 14;
 
+// What the first probe of an upsert reads from the home slot: the key words and the value word (KW <= 2) or the value
+// word with acquire order (KW >= 3). Loading it ahead of time (probe_load) lets a thread keep the home-slot loads of
+// several records in flight before it folds the first one.
+template <int KW> struct Probe { u64 w[KW <= 2 ? KW + 1 : 1]; };
+
 template <int KW>
-__device__ __forceinline__ u64 table_upsert(u64* __restrict__ table, u64 capacity, const u64 (&key)[KW], u64 add,
-                                            u32 mask, bool& is_new) {
+__device__ __forceinline__ void probe_load(const u64* s, Probe<KW>& p) {
+    if constexpr (KW == 1) {
+        ld_relaxed_v2(s, p.w[0], p.w[1]);
+    } else if constexpr (KW == 2) {
+        u64 pad;
+        ld_relaxed_v4(s, p.w[0], p.w[1], p.w[2], pad);
+    } else {
+        p.w[0] = ld_acquire(s + KW);
+    }
+}
+
+// `hl` is the key's local hash (local_hash(hash_key(key), n_ranks)); the home slot is slot_of(hl, capacity).
+// `first`, if given, holds what probe_load read from the home slot.
+template <int KW>
+__device__ __forceinline__ u64 table_upsert(u64* __restrict__ table, u64 capacity, u64 hl, const u64 (&key)[KW], u64 add,
+                                            u32 mask, bool& is_new, const Probe<KW>* first = nullptr) {
     constexpr int SW = SlotTraits<KW>::WORDS;
-    u64 slot = slot_of(hash_key<KW>(key), capacity);
+    u64 slot = slot_of(hl, capacity);
     is_new = false;
     u64 budget = PROBE_BUDGET;
+    bool pre = first != nullptr;
     if constexpr (KW == 1) {
-        for (; budget; --budget) {
+        for (; budget; --budget, pre = false) {
             u64* s = table + slot * SW;
             u64 cur, seen;
-            ld_relaxed_v2(s, cur, seen);  // key and value word: one 16-byte request
+            if (pre) { cur = first->w[0]; seen = first->w[1]; }
+            else ld_relaxed_v2(s, cur, seen);  // key and value word: one 16-byte request
             if (cur == EMPTY_WORD) {
+#if defined(GX_UP_VARIANT) && (GX_UP_VARIANT & 4)
+                // claim the slot and store the first occurrence's value with ONE 16-byte CAS (an empty slot's value is 0)
+                u64 o0, o1;
+                if (cas128(s, EMPTY_WORD, 0ull, key[0], add | ((u64)mask << MASK_SHIFT), o0, o1)) { is_new = true; return slot; }
+                cur = o0; seen = o1;
+#else
                 cur = atomicCAS(s, EMPTY_WORD, key[0]);
                 if (cur == EMPTY_WORD) { is_new = true; cur = key[0]; }
                 seen = 0;
+#endif
             }
             if (cur == key[0]) { fold_value(s + 1, add, mask, seen); return slot; }
             if (++slot == capacity) slot = 0;
         }
     } else if constexpr (KW == 2) {
-        for (; budget; --budget) {
+        for (; budget; --budget, pre = false) {
             u64* s = table + slot * SW;
             u64 c0, c1, seen, pad;
-            ld_relaxed_v4(s, c0, c1, seen, pad);  // the whole 32-byte slot (one sector)
+            if (pre) { c0 = first->w[0]; c1 = first->w[1]; seen = first->w[2]; }
+            else ld_relaxed_v4(s, c0, c1, seen, pad);  // the whole 32-byte slot (one sector)
             if (c0 == EMPTY_WORD && c1 == EMPTY_WORD) {
                 if (cas128(s, EMPTY_WORD, EMPTY_WORD, key[0], key[1], c0, c1)) { is_new = true; c0 = key[0]; c1 = key[1]; }
                 seen = 0;
@@ -103,10 +132,10 @@ __device__ __forceinline__ u64 table_upsert(u64* __restrict__ table, u64 capacit
             if (++slot == capacity) slot = 0;
         }
     } else {
-        for (; budget; --budget) {
+        for (; budget; --budget, pre = false) {
             u64* s = table + slot * SW;
             u64* vp = s + KW;
-            u64 v = ld_acquire(vp);
+            u64 v = pre ? first->w[0] : ld_acquire(vp);
             if (v == 0) {
                 if (atomicCAS(vp, 0ull, VAL_LOCK) == 0ull) {
 #pragma unroll
@@ -130,9 +159,9 @@ __device__ __forceinline__ u64 table_upsert(u64* __restrict__ table, u64 capacit
 
 // Find an existing key (after all inserts are complete). Returns capacity if absent.
 template <int KW>
-__device__ __forceinline__ u64 table_find(const u64* __restrict__ table, u64 capacity, const u64 (&key)[KW]) {
+__device__ __forceinline__ u64 table_find(const u64* __restrict__ table, u64 capacity, u64 hl, const u64 (&key)[KW]) {
     constexpr int SW = SlotTraits<KW>::WORDS;
-    u64 slot = slot_of(hash_key<KW>(key), capacity);
+    u64 slot = slot_of(hl, capacity);
     for (u64 probes = 0; probes < capacity; ++probes) {
         const u64* s = table + slot * SW;
         bool eq = true, empty;

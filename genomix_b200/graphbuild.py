@@ -27,8 +27,11 @@ class GenomixError(RuntimeError):
 
 class GraphBuilder:
     def __init__(self, kmer_length: int, device: int = 0, rank: int = 0, n_ranks: int = 1,
-                 expected_kmers: int = 0, chunk_bytes: int = 0, l2_fetch_granularity: int = 0,
-                 blocked_mode: int = 0, blocked_buckets: int = 0):
+                 expected_kmers: int = 0, chunk_bytes: int = 0, min_capacity: int = 0,
+                 start_small: bool = False, table_regions: int = 0):
+        """expected_kmers: optional hint (distinct k-mers this rank will own); chunk_bytes: internal chunk size;
+        min_capacity / start_small: smallest table and "no sizing heuristics" (tests of the growth path);
+        table_regions: regions of the region-sorted build (0 = sized for L2)."""
         self._lib = _lib.load()
         cfg = GxConfig()
         cfg.abi_version = _lib.GX_ABI_VERSION
@@ -38,9 +41,9 @@ class GraphBuilder:
         cfg.n_ranks = n_ranks
         cfg.expected_kmers = expected_kmers
         cfg.reserved[0] = chunk_bytes or int(os.environ.get("GENOMIX_GB_CHUNK", "0"))
-        cfg.reserved[1] = l2_fetch_granularity or int(os.environ.get("GENOMIX_GB_L2_GRAN", "0"))
-        cfg.reserved[2] = blocked_mode or int(os.environ.get("GENOMIX_GB_BLOCKED", "0"))   # 0 auto, 1 never, 2 always
-        cfg.reserved[3] = blocked_buckets or int(os.environ.get("GENOMIX_GB_BUCKETS", "0"))
+        cfg.reserved[1] = min_capacity
+        cfg.reserved[2] = 256 if start_small else 0
+        cfg.reserved[3] = table_regions or int(os.environ.get("GENOMIX_GB_REGIONS", "0"))
         self.kmer_length = kmer_length
         self._ctx = C.c_void_p()
         st = self._lib.gx_create(C.byref(cfg), C.byref(self._ctx))
@@ -205,7 +208,7 @@ class GraphBuilder:
         arr = (C.c_float * 8)()
         self._check(self._lib.gx_phase_ms(self._ctx, C.byref(arr)))
         return {"parse": arr[0], "insert": arr[1], "exchange": arr[2], "finish": arr[3], "h2d": arr[4],
-                "exchange_comm": arr[5], "exchange_insert": arr[6]}
+                "exchange_comm": arr[5], "exchange_insert": arr[6], "split": arr[7]}
 
     @property
     def kernel_launches(self) -> int:

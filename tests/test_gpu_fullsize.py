@@ -56,9 +56,10 @@ def test_cfg2_full_size_properties_and_fingerprint():
     stream, st = gpu_build_numpy(gx, w.k, text)
     assert st["kmer_occurrences"] == gx.synth.occurrences(w)
     fp = check_properties(stream, st, w.n_reads)
-    # invariance: other chunking, the L2-blocked build, and a table that has to grow several times
+    # invariance: other chunking, other region counts, a capacity hint, and a table that has to grow several times
     del stream
-    for kw in ({"chunk_bytes": 16 << 20}, {"blocked_mode": 2}, {"chunk_bytes": 48 << 20, "blocked_mode": 2, "blocked_buckets": 9}):
+    for kw in ({"chunk_bytes": 16 << 20}, {"table_regions": 9, "chunk_bytes": 48 << 20}, {"expected_kmers": 55_000_000},
+               {"start_small": True, "chunk_bytes": 64 << 20}):
         s2, st2 = gpu_build_numpy(gx, w.k, text, **kw)
         assert CO.canonical_fingerprint(s2).key() == fp.key(), kw
         del s2

@@ -72,21 +72,22 @@ def test_random_reads_match_oracle(k):
     assert got == oracle_canonical(k, text)
 
 
-@pytest.mark.parametrize("k,buckets", [(3, 2), (21, 7), (31, 64), (55, 5), (64, 1000), (91, 13), (128, 3)])
-def test_l2_blocked_build_matches_oracle(k, buckets):
-    """the L2-blocked path (flat extract -> partition by table region -> region-by-region insert), forced on a small
-    input, with growth in the middle of the region loop"""
+@pytest.mark.parametrize("k,regions", [(3, 2), (21, 7), (31, 64), (55, 5), (64, 1024), (91, 13), (128, 3)])
+def test_region_counts_match_oracle(k, regions):
+    """the region split with forced region counts (1 .. the multisplit's maximum) on a small input, whole and chunked,
+    with growth in the middle of the region walk"""
     gx = _gx()
     rng = np.random.default_rng(2000 + k)
     text = random_reads_text(rng, 300, k + 1, k + 60, paired=(k % 2 == 1), genome_len=max(3000, 30 * k))
     want = oracle_canonical(k, text)
-    got, _ = gpu_canonical(k, text, blocked_mode=2, blocked_buckets=buckets)
+    got, _ = gpu_canonical(k, text, table_regions=regions)
     assert got == want
-    got, _ = gpu_canonical(k, text, blocked_mode=2, blocked_buckets=buckets, chunk_bytes=3000)
+    got, _ = gpu_canonical(k, text, table_regions=regions, chunk_bytes=3000)
     assert got == want
-    with gx.GraphBuilder(k, blocked_mode=2, blocked_buckets=buckets, chunk_bytes=20000) as gb:
+    with gx.GraphBuilder(k, table_regions=regions, chunk_bytes=20000, min_capacity=8192, start_small=True) as gb:
         gb.push_lines(text)
         gb.finish()
+        assert gb.stats()["table_grows"] >= (1 if len(want) > 8192 else 0)
         assert gx.types.canonical_records(gb.records()) == want
 
 
@@ -122,7 +123,7 @@ def test_table_growth_rehash():
     rng = np.random.default_rng(6)
     text = random_reads_text(rng, 3000, 60, 100, genome_len=200000)
     want = oracle_canonical(31, text)
-    with gx.GraphBuilder(31, chunk_bytes=20000) as gb:
+    with gx.GraphBuilder(31, chunk_bytes=20000, min_capacity=8192) as gb:
         gb.push_lines(text)
         gb.finish()
         assert gb.stats()["table_grows"] >= 1
@@ -130,18 +131,25 @@ def test_table_growth_rehash():
 
 
 @pytest.mark.parametrize("k", [21, 55, 91])
-def test_spill_and_regrow_when_the_predictor_is_wrong(k):
-    """test hook (reserved[2] bit 8): the host assumes no occurrence is a new key, so the tiny initial table fills up
-    completely, upserts run out of probe budget, spill, and are re-inserted after the table has grown"""
+def test_deferral_and_regrow_when_the_table_starts_too_small(k):
+    """test hook (reserved[2] bit 8): no sizing heuristics, the table starts at 8192 slots for ~190k distinct keys: the
+    region upsert defers work items at the load limit, the host doubles the table and re-launches them, several times"""
     gx = _gx()
     rng = np.random.default_rng(77 + k)
     text = random_reads_text(rng, 4000, k + 20, k + 80, genome_len=400000)
     want = oracle_canonical_c(k, text)
-    with gx.GraphBuilder(k, blocked_mode=1 | 256, expected_kmers=1000) as gb:   # 65536-slot table, ~190k distinct keys
+    with gx.GraphBuilder(k, min_capacity=8192, start_small=True) as gb:
         gb.push_lines(text)
         gb.finish()
         st = gb.stats()
-        assert st["table_grows"] >= 1
+        assert st["table_grows"] >= 4
+        assert st["distinct_kmers"] <= 0.75 * st["table_capacity"]
+        assert gx.types.canonical_records(gb.records()) == want
+    # a wrong (far too small) hint is only a hint
+    with gx.GraphBuilder(k, expected_kmers=1000, min_capacity=8192) as gb:
+        gb.push_lines(text)
+        gb.finish()
+        assert gb.stats()["table_grows"] >= 1
         assert gx.types.canonical_records(gb.records()) == want
 
 
