@@ -404,7 +404,17 @@ int split_chunk(gx_ctx* c, const uint8_t* d_text, size_t n, u64 n_lines, u64 chu
 
 // K2: upsert regions [r0, r1) of the given record areas; grows the table and re-launches whatever the kernel deferred.
 // Leaves the stream synchronised and c->h_ctr current.
+int run_upsert_range(gx_ctx* c, const UpsertSrc* src, u32 n_src, u32 n_regions, u32 r0, u32 r1, u64 max_items);
+
 int run_upsert(gx_ctx* c, const UpsertSrc* src, u32 n_src, u32 n_regions, u32 r0, u32 r1, u64 max_items) {
+    // the kernel keeps the (region, source) pair descriptors of a launch in shared memory: at most UP_MAX_PAIRS of them
+    u32 step = std::max<u32>(1, UP_MAX_PAIRS / n_src);
+    if (const char* e = getenv("GENOMIX_GB_UPSERT_STEP")) step = std::max<u32>(1, std::min<u32>(step, (u32)atoi(e)));   // tuning
+    for (u32 r = r0; r < r1; r += step) GX_TRY(run_upsert_range(c, src, n_src, n_regions, r, std::min(r1, r + step), max_items));
+    return GX_OK;
+}
+
+int run_upsert_range(gx_ctx* c, const UpsertSrc* src, u32 n_src, u32 n_regions, u32 r0, u32 r1, u64 max_items) {
     UpsertArgs a{};
     for (u32 s = 0; s < n_src; ++s) a.src[s] = src[s];
     a.n_src = n_src; a.r0 = r0; a.r1 = r1; a.n_regions = n_regions; a.n_ranks = (u32)c->cfg.n_ranks;
@@ -418,7 +428,7 @@ int run_upsert(gx_ctx* c, const UpsertSrc* src, u32 n_src, u32 n_regions, u32 r0
     GX_TRY(check_launch(c, "upsert_prefix"));
     int cur = 0;
     u64 n_deferred = 0;
-    const unsigned ctas_per_sm = c->kw == 1 ? 2 : 1;
+    const u64 cta_warps = (u64)c->ops->upsert_warps;
     for (;;) {
         a.table = c->table; a.capacity = c->capacity;
         // Every warp in flight may add an item's worth of keys that ctr->distinct does not show yet, plus what it has not
@@ -426,9 +436,9 @@ int run_upsert(gx_ctx* c, const UpsertSrc* src, u32 n_src, u32 n_regions, u32 r0
         // limit. Small tables get fewer warps so that the margin stays a fraction of the limit.
         const u64 limit = (u64)(MAX_LOAD * (double)c->capacity);
         const u64 per_warp = UP_PUBLISH + 2 * UP_ITEM;
-        const u64 warps = std::max<u64>(1, std::min<u64>((u64)148 * ctas_per_sm * UP_WARPS, limit / (4 * per_warp)));
-        const unsigned grid = (unsigned)((warps + UP_WARPS - 1) / UP_WARPS);
-        a.active_warps = (u32)std::min<u64>(UP_WARPS, warps);
+        const u64 warps = std::max<u64>(1, std::min<u64>((u64)148 * c->ops->upsert_blocks * cta_warps, limit / (4 * per_warp)));
+        const unsigned grid = (unsigned)((warps + cta_warps - 1) / cta_warps);
+        a.active_warps = (u32)std::min<u64>(cta_warps, warps);
         a.hard_limit = limit - std::min<u64>(limit, (u64)grid * a.active_warps * per_warp);
         a.deferred_out = (u32*)c->deferred[cur].p;
         a.deferred_in = n_deferred ? (const u32*)c->deferred[cur ^ 1].p : nullptr;

@@ -14,6 +14,7 @@ namespace gx {
 // Host-callable launch table, one instance per KW (instantiated in gx_kw<N>.cu).
 struct EngineOps {
     int kw;
+    int upsert_warps, upsert_blocks;   // warps per CTA and CTAs per SM of the region upsert kernel
     size_t slot_bytes;
     size_t head_bytes;
     void (*init_table)(u64* table, u64 capacity, cudaStream_t st);

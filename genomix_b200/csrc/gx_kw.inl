@@ -17,7 +17,7 @@ void l_split_place(const SplitArgs& a, cudaStream_t st) {
     split_place_kernel<KW><<<grid_for(a.n_lines, SP_WARPS, 148 * SplitBlocks<KW>::MIN), SP_THREADS, sizeof(SplitSmem<KW>), st>>>(a);
 }
 void l_upsert_regions(const UpsertArgs& a, unsigned grid, cudaStream_t st) {
-    upsert_regions_kernel<KW><<<grid, UP_THREADS, sizeof(UpsertSmem<KW>), st>>>(a);
+    upsert_regions_kernel<KW><<<grid, UpsertCfg<KW>::THREADS, sizeof(UpsertSmem<KW>), st>>>(a);
 }
 void l_check_arena(const u64* keys, const u64* seg_start, u32 n_ranks, u32 n_regions, u64* bad, cudaStream_t st) {
     check_arena_kernel<KW><<<148 * 8, 256, 0, st>>>(keys, seg_start, n_ranks, n_regions, bad);
@@ -74,6 +74,8 @@ int l_prepare() {
 }
 
 const EngineOps OPS = {KW,
+                       UpsertCfg<KW>::WARPS,
+                       UpsertCfg<KW>::MIN_BLOCKS,
                        sizeof(u64) * SlotTraits<KW>::WORDS,
                        sizeof(Head<KW>),
                        l_init_table,

@@ -362,8 +362,16 @@ __global__ void __launch_bounds__(256) check_arena_kernel(const u64* __restrict_
 //   slow     the few queued records (about 6 % at load 0.4) are compacted into the low lanes and walk their probe
 //            sequences with the general table_upsert. Without the queue every warp would wait for the longest probe
 //            sequence among its 32 lanes, four times per item (measured: 3.7 dependent L2 round trips per record).
-static constexpr int UP_THREADS = 512;
-static constexpr int UP_WARPS = UP_THREADS / 32;
+#ifndef GX_UP_KW1_THREADS
+#define GX_UP_KW1_THREADS 256
+#define GX_UP_KW1_BLOCKS 3
+#endif
+// CTA shape per key width: what the register budget of the staged fast path allows
+template <int KW> struct UpsertCfg {
+    static constexpr int THREADS = (KW == 1) ? GX_UP_KW1_THREADS : 512;
+    static constexpr int MIN_BLOCKS = (KW == 1) ? GX_UP_KW1_BLOCKS : 1;
+    static constexpr int WARPS = THREADS / 32;
+};
 static constexpr int UP_PER_LANE = 4;
 static constexpr int UP_ITEM = 32 * UP_PER_LANE;             // records per work item
 static constexpr int UP_PUBLISH = 512;                       // a warp publishes its new-key count at the latest after this many
@@ -415,71 +423,110 @@ static __global__ void __launch_bounds__(1024) upsert_prefix_kernel(UpsertArgs a
     if (threadIdx.x == 0) item_prefix[n_pairs] = (u32)carry_s;
 }
 
-template <int KW> struct UpsertBlocks { static constexpr int MIN = (KW == 1) ? 2 : 1; };
+static constexpr int UP_MAX_PAIRS = 2048;   // (region, source) pairs of one launch: their descriptors live in shared memory
 
 template <int KW>
 struct UpsertSmem {
-    u64 qkeys[UP_WARPS][UP_ITEM * KW];       // per-warp slow queue
-    unsigned short qmeta[UP_WARPS][UP_ITEM];
+    u64 qkeys[UpsertCfg<KW>::WARPS][UP_ITEM * KW];       // per-warp slow queue
+    u64 first[UP_MAX_PAIRS];                 // record index (in the pair's source area) of the pair's first record
+    u32 prefix[UP_MAX_PAIRS + 1];            // exclusive prefix of work items per pair
+    u32 count[UP_MAX_PAIRS];                 // records of the pair
+    unsigned short qmeta[UpsertCfg<KW>::WARPS][UP_ITEM];
 };
 
 template <int KW>
-__global__ void __launch_bounds__(UP_THREADS, UpsertBlocks<KW>::MIN) upsert_regions_kernel(UpsertArgs a) {
+__global__ void __launch_bounds__(UpsertCfg<KW>::THREADS, UpsertCfg<KW>::MIN_BLOCKS) upsert_regions_kernel(UpsertArgs a) {
+    constexpr int UP_THREADS = UpsertCfg<KW>::THREADS;
     constexpr int SW = SlotTraits<KW>::WORDS;
+    constexpr bool PREFETCH = KW <= 2;   // the next item's records are loaded while the current one is applied
     extern __shared__ __align__(16) unsigned char upsert_smem_raw[];
     UpsertSmem<KW>& Q = *reinterpret_cast<UpsertSmem<KW>*>(upsert_smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 n_pairs = (a.r1 - a.r0) * a.n_src;
+    for (u32 p = threadIdx.x; p <= n_pairs; p += UP_THREADS) {
+        Q.prefix[p] = a.item_prefix[p];
+        if (p < n_pairs) {
+            const UpsertSrc& S = a.src[p % a.n_src];
+            const u32 region = a.r0 + p / a.n_src;
+            const u64 lo = S.seg[region];
+            Q.first[p] = lo - (S.rebase ? S.seg[0] : 0ull);
+            Q.count[p] = (u32)(S.seg[region + 1] - lo);
+        }
+    }
+    __syncthreads();
     if ((u32)warp >= a.active_warps) return;
     const u32 lane_lt = (1u << lane) - 1u;
     u64* qk = Q.qkeys[warp];
     unsigned short* qm = Q.qmeta[warp];
-    const u32 n_pairs = (a.r1 - a.r0) * a.n_src;
-    const u32 total = a.deferred_in ? a.n_deferred_in : a.item_prefix[n_pairs];
+    const u32 total = a.deferred_in ? a.n_deferred_in : Q.prefix[n_pairs];
     const u32 gw = blockIdx.x * a.active_warps + warp, n_gw = gridDim.x * a.active_warps;
     u32 pair = 0;
     u32 unpublished = 0;                                 // slots this warp created and has not added to ctr->distinct yet
     u64 next_distinct = ld_relaxed(&a.ctr->distinct);    // refreshed one item ahead, so the load never stalls the warp
-    for (u32 w = gw; w < total; w += n_gw) {
+
+    // work item w -> its id t, its records and how many there are (n == 0: no such item)
+    u64 nkey[UP_PER_LANE][KW];
+    u32 nm[UP_PER_LANE];
+    u32 nn = 0, nt = 0;
+    auto fetch = [&](u32 w) {
+        nn = 0;
+        if (w >= total) return;
         u32 t = w;
         if (a.deferred_in) {
             t = a.deferred_in[w];
-            u32 lo = 0, hi = n_pairs - 1;   // largest pair with item_prefix[pair] <= t
+            u32 lo = 0, hi = n_pairs - 1;   // largest pair with prefix[pair] <= t
             while (lo < hi) {
                 const u32 mid = (lo + hi + 1) >> 1;
-                if (a.item_prefix[mid] <= t) lo = mid; else hi = mid - 1;
+                if (Q.prefix[mid] <= t) lo = mid; else hi = mid - 1;
             }
             pair = lo;
         }
-        while (t >= a.item_prefix[pair + 1]) ++pair;   // skips empty pairs
+        while (t >= Q.prefix[pair + 1]) ++pair;   // skips empty pairs
+        const u32 item_off = (t - Q.prefix[pair]) * UP_ITEM;
+        const u64 first = Q.first[pair] + item_off;
+        const UpsertSrc& S = a.src[pair % a.n_src];
+        const u64* keys = S.keys + first * KW;
+        const unsigned short* meta = S.meta + first;
+        nt = t;
+        nn = min((u32)UP_ITEM, Q.count[pair] - item_off);
+#pragma unroll
+        for (int i = 0; i < UP_PER_LANE; ++i) {
+            const u32 r = lane + 32u * i;
+            if (r < nn) {
+#pragma unroll
+                for (int j = 0; j < KW; ++j) nkey[i][j] = __ldcs(keys + (u64)r * KW + j);   // streamed once: evict first
+                nm[i] = __ldcs(meta + r);
+            }
+        }
+    };
+    fetch(gw);
+    for (u32 w = gw; w < total; w += n_gw) {
+        u64 key[UP_PER_LANE][KW];
+        u32 m[UP_PER_LANE];
+        const u32 n = nn, t = nt;
+#pragma unroll
+        for (int i = 0; i < UP_PER_LANE; ++i) {
+            m[i] = nm[i];
+#pragma unroll
+            for (int j = 0; j < KW; ++j) key[i][j] = nkey[i][j];
+        }
+        if constexpr (PREFETCH) fetch(w + n_gw);
         // apply the item only while the table has room for everything that all warps in flight could still add
         // (hard_limit leaves that margin); otherwise hand it back to the host, which grows the table
         const u64 distinct_now = next_distinct;
         next_distinct = ld_relaxed(&a.ctr->distinct);
         if (distinct_now > a.hard_limit) {
             if (lane == 0) a.deferred_out[atomicAdd(&a.ctr->deferred_count, 1ull)] = t;
+            if constexpr (!PREFETCH) fetch(w + n_gw);
             continue;
         }
-        const u32 region = a.r0 + pair / a.n_src, s = pair % a.n_src;
-        const UpsertSrc& S = a.src[s];
-        const u64 seg_lo = S.seg[region], count = S.seg[region + 1] - seg_lo;
-        const u64 item_off = (u64)(t - a.item_prefix[pair]) * UP_ITEM;
-        const u64 first = seg_lo - (S.rebase ? S.seg[0] : 0ull) + item_off;
-        const u32 n = (u32)min((u64)UP_ITEM, count - item_off);
-        const u64* keys = S.keys + first * KW;
-        const unsigned short* meta = S.meta + first;
 
-        // ---- stage 1: records and home-slot snapshots
-        u64 key[UP_PER_LANE][KW];
-        u32 m[UP_PER_LANE];
+        // ---- stage 1: home-slot snapshots of the item's records
         u64* sp[UP_PER_LANE];
         Probe<KW> pr[UP_PER_LANE];
 #pragma unroll
         for (int i = 0; i < UP_PER_LANE; ++i) {
-            const u32 r = lane + 32u * i;
-            if (r < n) {
-#pragma unroll
-                for (int j = 0; j < KW; ++j) key[i][j] = __ldcs(keys + (u64)r * KW + j);   // streamed once: evict first
-                m[i] = __ldcs(meta + r);
+            if (lane + 32u * i < n) {
                 sp[i] = a.table + slot_of(local_hash(hash_key<KW>(key[i]), a.n_ranks), a.capacity) * SW;
                 probe_load<KW>(sp[i], pr[i]);
             }
@@ -497,7 +544,9 @@ __global__ void __launch_bounds__(UP_THREADS, UpsertBlocks<KW>::MIN) upsert_regi
                 if (eq) fold_value(sp[i] + KW, 1ull, m[i], pr[i].w[KW]);
                 else if (empty) {
                     claim |= 1u << i;
-                    if constexpr (KW == 1) { old0[i] = atomicCAS(sp[i], EMPTY_WORD, key[i][0]); old1[i] = 0; }
+                    // KW == 1: key and value word share one 16-byte slot, so ONE 128-bit CAS claims the slot and stores the
+                    // first occurrence's count and edge bits (an empty slot's value word is 0): 1 atomic instead of 3
+                    if constexpr (KW == 1) (void)cas128(sp[i], EMPTY_WORD, 0ull, key[i][0], 1ull | ((u64)m[i] << MASK_SHIFT), old0[i], old1[i]);
                     else (void)cas128(sp[i], EMPTY_WORD, EMPTY_WORD, key[i][0], key[i][1], old0[i], old1[i]);
                 } else slow |= 1u << i;
             }
@@ -505,10 +554,16 @@ __global__ void __launch_bounds__(UP_THREADS, UpsertBlocks<KW>::MIN) upsert_regi
 #pragma unroll
             for (int i = 0; i < UP_PER_LANE; ++i) {
                 if (!((claim >> i) & 1u)) continue;
-                const bool won = old0[i] == EMPTY_WORD && (KW == 1 || old1[i] == EMPTY_WORD);
-                const bool same = old0[i] == key[i][0] && (KW == 1 || old1[i] == key[i][KW - 1]);   // lost to the same key
-                if (won || same) { fold_value(sp[i] + KW, 1ull, m[i], 0ull); n_new += won ? 1u : 0u; }
-                else slow |= 1u << i;
+                if constexpr (KW == 1) {
+                    if (old0[i] == EMPTY_WORD) ++n_new;                                                 // won: nothing left to do
+                    else if (old0[i] == key[i][0]) fold_value(sp[i] + 1, 1ull, m[i], old1[i]);         // lost to the same key
+                    else slow |= 1u << i;
+                } else {
+                    const bool won = old0[i] == EMPTY_WORD && old1[i] == EMPTY_WORD;
+                    const bool same = old0[i] == key[i][0] && old1[i] == key[i][1];   // lost to the same key
+                    if (won || same) { fold_value(sp[i] + KW, 1ull, m[i], 0ull); n_new += won ? 1u : 0u; }
+                    else slow |= 1u << i;
+                }
             }
         } else {
             // claim protocol: val 0 -> LOCK, write key words, publish val with release order
@@ -578,6 +633,7 @@ __global__ void __launch_bounds__(UP_THREADS, UpsertBlocks<KW>::MIN) upsert_regi
             if (lane == 0) atomicAdd(&a.ctr->distinct, (u64)unpublished);
             unpublished = 0;
         }
+        if constexpr (!PREFETCH) fetch(w + n_gw);
     }
     if (lane == 0 && unpublished) atomicAdd(&a.ctr->distinct, (u64)unpublished);
 }

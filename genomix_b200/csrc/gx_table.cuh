@@ -104,16 +104,10 @@ __device__ __forceinline__ u64 table_upsert(u64* __restrict__ table, u64 capacit
             if (pre) { cur = first->w[0]; seen = first->w[1]; }
             else ld_relaxed_v2(s, cur, seen);  // key and value word: one 16-byte request
             if (cur == EMPTY_WORD) {
-#if defined(GX_UP_VARIANT) && (GX_UP_VARIANT & 4)
                 // claim the slot and store the first occurrence's value with ONE 16-byte CAS (an empty slot's value is 0)
                 u64 o0, o1;
                 if (cas128(s, EMPTY_WORD, 0ull, key[0], add | ((u64)mask << MASK_SHIFT), o0, o1)) { is_new = true; return slot; }
                 cur = o0; seen = o1;
-#else
-                cur = atomicCAS(s, EMPTY_WORD, key[0]);
-                if (cur == EMPTY_WORD) { is_new = true; cur = key[0]; }
-                seen = 0;
-#endif
             }
             if (cur == key[0]) { fold_value(s + 1, add, mask, seen); return slot; }
             if (++slot == capacity) slot = 0;

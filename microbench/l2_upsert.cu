@@ -33,6 +33,7 @@ __device__ __forceinline__ bool cas128(u64* addr, u64 c0, u64 c1, u64 n0, u64 n1
 
 // MODE 0: ld only   1: ld + RED.add   2: ld + RED.add + RED.or   3: real upsert (empty -> CAS64 + add + or; else add, or if new bits)
 //      4: real upsert with a 128-bit CAS claiming key and value at once   5: RED.add only (no load)
+//      6: ld + 32-bit RED.add   7: 32-bit RED.add only
 template <int MODE, int PER>
 __global__ void __launch_bounds__(512) k_upsert(u64* table, const u64* __restrict__ rec, u64 n, u64 slots, u32 n_regions, u64 per_region,
                                                 int prefetch, u64* out) {
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(512) k_upsert(u64* table, const u64* __restric
         for (int i = 0; i < PER; ++i) {
             const u64 idx = first + tid + (u64)i * 512;
             s[i] = idx < n ? __ldcs(rec + idx) : ~0ull;
-            if (MODE != 5 && s[i] != ~0ull) ld_v2(table + 2 * s[i], k[i], v[i]);
+            if (MODE != 5 && MODE != 7 && s[i] != ~0ull) ld_v2(table + 2 * s[i], k[i], v[i]);
         }
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(512) k_upsert(u64* table, const u64* __restric
             const u64 key = s[i] * 2 + 1, m = (mix64(s[i]) & 3) + 1;   // the slot's key; a few distinct masks per key
             if (MODE == 0) acc ^= k[i] ^ v[i];
             if (MODE == 1 || MODE == 5) { atomicAdd(p + 1, 1ull); if (MODE == 1) acc ^= k[i]; }
+            if (MODE == 6 || MODE == 7) { atomicAdd(reinterpret_cast<u32*>(p + 1), 1u); if (MODE == 6) acc ^= k[i]; }
             if (MODE == 2) { atomicAdd(p + 1, 1ull); atomicOr(p + 1, m << 48); acc ^= k[i]; }
             if (MODE == 3) {
                 u64 cur = k[i], seen = v[i];
@@ -95,16 +97,16 @@ int main(int argc, char** argv) {
     u64 *table, *rec, *out;
     cudaMalloc(&table, slots * 16); cudaMalloc(&rec, n * 8); cudaMalloc(&out, 8);
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-    const char* names[] = {"ld only", "ld+RED.add", "ld+RED.add+RED.or", "upsert CAS64", "upsert CAS128", "RED.add only"};
+    const char* names[] = {"ld only", "ld+RED.add", "ld+RED.add+RED.or", "upsert CAS64", "upsert CAS128", "RED.add only", "ld+RED.add.32", "RED.add.32 only"};
     printf("table %llu MB, %llu records, distinct fraction %.2f\n", table_mb, n, distinct_frac);
-    const int region_mb[] = {2, 4, 8, 16, 24, 32, 48, 64, 128, (int)table_mb};
-    for (int ri = 0; ri < 10; ++ri) {
+    const int region_mb[] = {4, 32, 128};
+    for (int ri = 0; ri < 3; ++ri) {
         const u32 n_regions = (u32)(table_mb / region_mb[ri]);
         if (n_regions == 0) continue;
         const u64 per_region = (n / n_regions) / 8192 * 8192, nn = per_region * n_regions;
         gen_records<<<148 * 8, 256>>>(rec, nn, slots, n_regions, per_region, (u64)(per_region * distinct_frac) + 1);
-        for (int mode = 0; mode < 6; ++mode) {
-            for (int cfg = 0; cfg < 3; ++cfg) {   // 0: 2 CTA/SM no prefetch, 1: 2 CTA/SM prefetch, 2: 4 CTA/SM... (1 CTA of 512 = 16 warps)
+        for (int mode = 0; mode < 8; ++mode) {
+            for (int cfg = 0; cfg < 3; cfg += 2) {   // 0: 2 CTA/SM no prefetch, 1: 2 CTA/SM prefetch, 2: 4 CTA/SM... (1 CTA of 512 = 16 warps)
                 const int grid = 148 * (cfg == 2 ? 4 : 2), prefetch = cfg == 1;
                 float best = 1e9;
                 for (int rep = 0; rep < 2; ++rep) {
@@ -117,6 +119,8 @@ int main(int argc, char** argv) {
                         case 3: k_upsert<3, 4><<<grid, 512>>>(table, rec, nn, slots, n_regions, per_region, prefetch, out); break;
                         case 4: k_upsert<4, 4><<<grid, 512>>>(table, rec, nn, slots, n_regions, per_region, prefetch, out); break;
                         case 5: k_upsert<5, 4><<<grid, 512>>>(table, rec, nn, slots, n_regions, per_region, prefetch, out); break;
+                        case 6: k_upsert<6, 4><<<grid, 512>>>(table, rec, nn, slots, n_regions, per_region, prefetch, out); break;
+                        case 7: k_upsert<7, 4><<<grid, 512>>>(table, rec, nn, slots, n_regions, per_region, prefetch, out); break;
                     }
                     cudaEventRecord(b); cudaEventSynchronize(b);
                     float ms; cudaEventElapsedTime(&ms, a, b);
