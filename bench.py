@@ -139,7 +139,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "kmer_occurrences_per_sec_graph_build", "value": value, "unit": "kmers/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": workload_desc(base, 1), "k": base.k, "read_len": base.read_len},
+        "config": {"workload": workload_desc(base, 1), "k": base.k, "read_len": base.read_len, "sample": sample},
         "bases_per_sec": n_sample * base.read_len * (2 if base.paired else 1) * args.steps / dt,
         "cpu_baseline": {"value": value, "unit": "kmers/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "kmers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -154,6 +154,166 @@ def workload_desc(w, world):
     return s
 
 
+def line_aligned_chunks(text_np, chunk_bytes):
+    """[(offset, length)] of whole-line chunks of at most chunk_bytes (host-side; the pushes themselves are device-side)."""
+    n = int(text_np.size)
+    out, pos = [], 0
+    while pos < n:
+        end = min(n, pos + chunk_bytes)
+        if end < n:
+            back = np.flatnonzero(text_np[max(pos, end - (1 << 16)):end] == 10)
+            if back.size:
+                end = max(pos, end - (1 << 16)) + int(back[-1]) + 1
+        out.append((pos, end - pos))
+        pos = end
+    return out
+
+
+class Job:
+    """One workload resident on this rank's GPU plus the GraphBuilder that builds it."""
+
+    def __init__(self, gx, torch, dist, dev, local_rank, rank, world, w, text_np, hint, uid=None, chunk_bytes=256 << 20):
+        self.torch, self.dist, self.world, self.dev = torch, dist, world, dev
+        self.w = w
+        self.host_text = torch.from_numpy(text_np).pin_memory()
+        self.dev_text = self.host_text.to(dev, non_blocking=False)
+        self.gb = gx.GraphBuilder(w.k, device=local_rank, rank=rank, n_ranks=world, expected_kmers=hint, chunk_bytes=chunk_bytes)
+        self.stream = torch.cuda.current_stream(dev)
+        self.gb.set_stream(self.stream.cuda_stream)
+        self.chunks = line_aligned_chunks(text_np, chunk_bytes) if world > 1 else [(0, int(text_np.size))]
+        self.rounds = len(self.chunks)
+        if world > 1:
+            uid = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                uid = torch.from_numpy(self.gb.mg_unique_id().copy())
+            uid = uid.to(dev)
+            dist.broadcast(uid, 0)
+            self.gb.mg_init(uid.cpu().numpy())
+            t = torch.tensor([self.rounds], device=dev, dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            self.rounds = int(t.item())
+
+    def step_device(self):
+        """reads resident in HBM -> records resident in HBM; N > 1: one collective exchange round per chunk"""
+        gb = self.gb
+        gb.reset()
+        base = self.dev_text.data_ptr()
+        for i in range(self.rounds):
+            if i < len(self.chunks):
+                off, ln = self.chunks[i]
+                gb.push_lines_device(base + off, ln)
+            if self.world > 1:
+                gb.mg_exchange()
+        gb.finish()
+
+    def step_host(self, out_host):
+        """pinned host text -> records in pinned host memory (H2D and D2H inside)"""
+        import ctypes as C
+        gb = self.gb
+        gb.reset()
+        for i in range(self.rounds):
+            if i < len(self.chunks):
+                off, ln = self.chunks[i]
+                gb.push_lines(self.host_text[off:off + ln])
+            if self.world > 1:
+                gb.mg_exchange()
+        gb.finish()
+        n = gb.record_bytes
+        cursor, used, pos = C.c_uint64(0), C.c_size_t(0), 0
+        while pos < n:
+            gb._check(gb._lib.gx_next_records(gb._ctx, C.byref(cursor), C.c_void_p(out_host.data_ptr() + pos),
+                                               out_host.numel() - pos, C.byref(used)))
+            if used.value == 0:
+                break
+            pos += used.value
+        return pos
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def timed(self, steps, warmup):
+        """(ms per step, max over ranks; per-phase ms per step; launches per step; stats)"""
+        torch = self.torch
+        for _ in range(warmup):
+            self.step_device()
+        stats = self.gb.stats()
+        self.barrier()
+        launches0 = self.gb.kernel_launches
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        phase_acc = {}
+        ev0.record(self.stream)
+        for _ in range(steps):
+            self.step_device()
+            for key, val in self.gb.phase_ms().items():
+                phase_acc[key] = phase_acc.get(key, 0.0) + val
+        ev1.record(self.stream)
+        self.barrier()
+        ms = ev0.elapsed_time(ev1) / steps
+        launches = (self.gb.kernel_launches - launches0) / steps
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.dev, dtype=torch.float64)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, {k_: v / steps for k_, v in phase_acc.items()}, launches, stats
+
+    def allsum(self, *vals):
+        if self.world == 1:
+            return [float(v) for v in vals]
+        t = self.torch.tensor([float(v) for v in vals], device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [float(x) for x in t.tolist()]
+
+    def close(self):
+        self.gb.close()
+        del self.dev_text, self.host_text
+
+
+def parity_pass(gx, torch, dist, dev, local_rank, rank, world, name, factor):
+    """Untimed multi-GPU parity check: a 1/factor twin of `name` is built by all ranks from line shards of the same text;
+    the ranks' order-independent canonical fingerprints (oracle/gx_oracle.c, additive over disjoint record sets) are
+    summed and compared with the C oracle's fingerprint of the whole text on rank 0."""
+    from oracle import c_oracle as CO
+    from genomix_b200 import multigpu
+    w = gx.synth.scaled(gx.synth.CONFIGS[name], factor)
+    text = gx.synth.readid_text(w)
+    shard = multigpu.shard_lines(text, rank, world)
+    job = Job(gx, torch, dist, dev, local_rank, rank, world, w, np.ascontiguousarray(shard), 0, chunk_bytes=max(1 << 20, shard.size // 3 + 1))
+    job.step_device()
+    stream = np.frombuffer(job.gb.records(), dtype=np.uint8)
+    fp = CO.canonical_fingerprint(stream)
+    st = job.gb.stats()
+    job.close()
+    ints = torch.tensor([fp.sum & 0xffffffff, fp.sum >> 32, fp.records, fp.heads, fp.edges, int(fp.coverage_total), st["kmer_occurrences"]],
+                        device=dev, dtype=torch.int64)
+    gathered = [torch.zeros_like(ints) for _ in range(world)]
+    dist.all_gather(gathered, ints)
+    xors = torch.tensor([fp.xor & 0x7fffffffffffffff, fp.xor >> 63], device=dev, dtype=torch.int64)
+    xg = [torch.zeros_like(xors) for _ in range(world)]
+    dist.all_gather(xg, xors)
+    out = None
+    if rank == 0:
+        tot = [0] * 7
+        x = 0
+        for g, xx in zip(gathered, xg):
+            v = [int(t) for t in g.tolist()]
+            tot = [a + b for a, b in zip(tot, v)]
+            lo, hi = (int(t) for t in xx.tolist())
+            x ^= lo | (hi << 63)
+        got_sum = ((tot[0] + (tot[1] << 32)) & 0xffffffffffffffff)
+        want_stream, ost = CO.build_graph_records(w.k, text, os.cpu_count() or 1, as_numpy=True)
+        wfp = CO.canonical_fingerprint(want_stream)
+        ok = (got_sum == wfp.sum and x == wfp.xor and tot[2] == wfp.records and tot[3] == wfp.heads and tot[4] == wfp.edges
+              and tot[5] == int(wfp.coverage_total) and tot[6] == ost["occurrences"])
+        out = {"ok": bool(ok), "workload": f"{name}/{factor:g} (k={w.k}, {w.n_reads} reads, {ost['occurrences']} k-mer occurrences)",
+               "records": tot[2], "oracle_records": int(wfp.records), "read_heads": tot[3], "edges": tot[4], "n_ranks": world,
+               "check": "sum/xor of per-record 64-bit hashes (key, neighbour sets, read-head lists, coverage) over all ranks == C oracle"}
+    flag = torch.tensor([1 if (out is None or out["ok"]) else 0], device=dev)
+    dist.broadcast(flag, 0)
+    return out, bool(flag.item())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -161,10 +321,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--target-workload", default="cfg4", help="N>1: second, strong-scaled full-size workload (BASELINE configs[3]); 'none' skips it")
+    ap.add_argument("--target-steps", type=int, default=2)
     ap.add_argument("--ref-sample-reads", type=int, default=60000)
     ap.add_argument("--cpu-sample-reads", type=int, default=100000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-nohint", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -187,135 +351,128 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    # ---- multi-GPU parity, untimed, before anything is measured: k=55 twin of the target workload
+    parity = None
+    if world > 1 and not args.no_parity:
+        parity, ok = parity_pass(gx, torch, dist, dev, local_rank, rank, world, "cfg4", 100)
+        if not ok:
+            if rank == 0:
+                print(json.dumps({"metric": "kmer_occurrences_per_sec_graph_build", "value": None, "parity": parity}), flush=True)
+            dist.destroy_process_group()
+            raise SystemExit("bench.py: multi-GPU parity check FAILED")
+
     w, text_np, n_reads = make_workload(args.workload, rank, world)
     n_occ = gx.synth.occurrences(w, n_reads)
     n_bases = n_reads * w.read_len * (2 if w.paired else 1)
-    host_text = torch.from_numpy(text_np).pin_memory()
-    dev_text = host_text.to(dev, non_blocking=False)
     hint = expected_distinct(w, n_reads * world) // world
-
-    gb = gx.GraphBuilder(w.k, device=local_rank, rank=rank, n_ranks=world, expected_kmers=hint)
-    stream = torch.cuda.current_stream(dev)
-    gb.set_stream(stream.cuda_stream)
-    if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            uid = torch.from_numpy(gb.mg_unique_id().copy())
-        uid = uid.to(dev)
-        dist.broadcast(uid, 0)
-        gb.mg_init(uid.cpu().numpy())
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def step_device():
-        gb.reset()
-        gb.push_lines_device(dev_text.data_ptr(), dev_text.numel())
-        if world > 1:
-            gb.mg_exchange()
-        gb.finish()
+    job = Job(gx, torch, dist, dev, local_rank, rank, world, w, text_np, hint)
+    gb = job.gb
 
     sampler = ClockSampler(local_rank)
     sampler.start()  # started before the warm-up so that short timed regions still get samples (all under load)
-    for _ in range(args.warmup):
-        step_device()
-    stats = gb.stats()
-    barrier()
-    launches0 = gb.kernel_launches
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    phase_acc = {}
-    ev0.record(stream)
-    for _ in range(args.steps):
-        step_device()
-        for key, val in gb.phase_ms().items():
-            phase_acc[key] = phase_acc.get(key, 0.0) + val
-    ev1.record(stream)
-    barrier()
+    ms_per_step, phase, launches, stats = job.timed(args.steps, args.warmup)
     clocks = sampler.stop()
-    ms_total = ev0.elapsed_time(ev1)
-    launches = gb.kernel_launches - launches0
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-        agg = torch.tensor([float(n_occ), float(n_bases), float(stats["distinct_kmers"]), float(launches)], device=dev,
-                           dtype=torch.float64)
-        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-        tot_occ, tot_bases, tot_distinct, launches = (float(x) for x in agg.tolist())
-    else:
-        tot_occ, tot_bases, tot_distinct = float(n_occ), float(n_bases), float(stats["distinct_kmers"])
-    ms_per_step = ms_total / args.steps
+    tot_occ, tot_bases, tot_distinct, launches = job.allsum(n_occ, n_bases, stats["distinct_kmers"], launches)
     value = tot_occ / (ms_per_step * 1e-3)
 
-    # ---- roofline of the dominant kernel (extract+insert), timed live with CUDA events inside the library
+    # ---- roofline, timed live with CUDA events inside the library (gx_phase_ms), per rank 0
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    job_bytes, insert_bytes, b_occ, b_dist = algorithmic_bytes(w.k, w.read_len, n_occ, stats["distinct_kmers"])
-    insert_ms = (phase_acc.get("insert", 0.0) + phase_acc.get("split", 0.0)) / args.steps
-    traffic = None
+    kb = kb_of(w.k)
+    n_up = stats["distinct_kmers"]            # keys this rank's table ends up with
+    rank_occ = tot_occ / world                  # records this rank upserts (own + received; hash-uniform)
+    job_bytes, build_bytes, b_occ, b_dist = algorithmic_bytes(w.k, w.read_len, n_occ, n_up)
+    upsert_ms = phase.get("insert", 0.0) + phase.get("exchange_insert", 0.0)
+    build_ms = upsert_ms + phase.get("split", 0.0)
+    upsert_bytes = rank_occ * (kb + 16) + n_up * kb     # per occurrence: its key + the 16-byte slot update; per new key: the key
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if world == 1 and os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(f"{args.workload}_extract_insert_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj.get(f"{args.workload}_upsert_regions_bytes_per_step"), tj.get(f"{args.workload}_upsert_regions_source")
         except Exception:
             traffic = None
-    n_insert_launches = max(1, -(-dev_text.numel() // (64 << 20)))
     roof = {
-        "bound": "hbm", "kernel": "extract_kernel<KW,EX_UPSERT> (k-mer extract + hash upsert)" if world == 1 else
-        "extract_kernel<KW,EX_ROUTE> (k-mer extract + own-key upsert + routing); received keys: insert_records_kernel",
-        "achieved": insert_bytes / (insert_ms * 1e-3) / 1e9 if insert_ms > 0 else None,
+        "bound": "hbm", "kernel": "upsert_regions_kernel<KW> (region-sorted k-mer records -> hash-table upserts)",
+        "achieved": upsert_bytes / (upsert_ms * 1e-3) / 1e9 if upsert_ms > 0 else None,
         "peak": peak, "unit": "GB/s", "peak_source": peak_src,
-        "frac": (insert_bytes / (insert_ms * 1e-3) / 1e9 / peak) if insert_ms > 0 else None,
-        "traffic": traffic,
-        "algorithmic_bytes_per_step": insert_bytes, "kernel_ms_per_step": insert_ms,
-        "launches_per_step": n_insert_launches,
-        "bytes_per_occurrence": b_occ, "job_bytes_per_step": job_bytes,
+        "frac": (upsert_bytes / (upsert_ms * 1e-3) / 1e9 / peak) if upsert_ms > 0 else None,
+        "traffic": traffic, "traffic_source": traffic_src,
+        "algorithmic_bytes_per_step": upsert_bytes, "kernel_ms_per_step": upsert_ms,
+        "launches_per_step": max(1, job.rounds),
+        "bytes_per_occurrence": kb + 16,
+        "build_phase": {"kernels": "split_count + split_place + upsert_regions (what round 1's fused extract_kernel did)",
+                        "algorithmic_bytes_per_step": build_bytes, "ms_per_step": build_ms, "bytes_per_occurrence": b_occ,
+                        "frac": build_bytes / (build_ms * 1e-3) / 1e9 / peak if build_ms > 0 else None},
+        "job_bytes_per_step": job_bytes,
         "job_frac": job_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
     }
+    nvlink = None
+    if world > 1:
+        comm_ms = phase.get("exchange_comm", 0.0)
+        sent = rank_occ * (world - 1) / world * (kb + 2)
+        nvlink = {"bytes_sent_per_rank_per_step": sent, "exchange_comm_ms": comm_ms,
+                  "achieved_GBps_per_direction": sent / (comm_ms * 1e-3) / 1e9 if comm_ms > 0 else None,
+                  "peak_GBps_per_direction": 900.0, "frac": sent / (comm_ms * 1e-3) / 1e9 / 900.0 if comm_ms > 0 else None,
+                  "formula": "N/G * (G-1)/G * (Kb+2) bytes (BASELINE.md §3) / exchange_comm (copy-engine pushes, CUDA events on the comm stream)"}
 
     # ---- e2e through the host API: pinned text in, whole record stream out
     e2e = None
     if not args.no_e2e:
-        import ctypes as C
         rec_bytes = gb.record_bytes
         out_host = torch.empty(max(rec_bytes, 1) + (1 << 20), dtype=torch.uint8).pin_memory()
-
-        def step_host():
-            gb.reset()
-            gb.push_lines(host_text)
-            if world > 1:
-                gb.mg_exchange()
-            gb.finish()
-            n = gb.record_bytes
-            cursor, used, pos = C.c_uint64(0), C.c_size_t(0), 0
-            while pos < n:
-                gb._check(gb._lib.gx_next_records(gb._ctx, C.byref(cursor), C.c_void_p(out_host.data_ptr() + pos),
-                                                   out_host.numel() - pos, C.byref(used)))
-                if used.value == 0:
-                    break
-                pos += used.value
-            return pos
-
-        step_host()
-        barrier()
+        job.step_host(out_host)
+        job.barrier()
         t0 = time.perf_counter()
         e_steps = max(1, min(args.steps, 3))
         d2h = 0
         for _ in range(e_steps):
-            d2h = step_host()
-        barrier()
+            d2h = job.step_host(out_host)
+        job.barrier()
         dt = time.perf_counter() - t0
         if world > 1:
             t = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        e2e = {"value": tot_occ * e_steps / dt, "unit": "kmers/s", "h2d_bytes_per_step": int(host_text.numel()),
+        e2e = {"value": tot_occ * e_steps / dt, "unit": "kmers/s", "h2d_bytes_per_step": int(job.host_text.numel()),
                "d2h_bytes_per_step": int(d2h), "steps": e_steps, "timing": "wall clock between synchronises"}
+        del out_host
+    table_info = {"capacity": stats["table_capacity"], "grows": stats["table_grows"], "expected_kmers_hint": hint,
+                  "load": stats["distinct_kmers"] / max(1, stats["table_capacity"])}
+    job.close()
+
+    # ---- the same build without the capacity hint (the reference CLI has no such option): the table is sized from a pilot
+    nohint = None
+    if world == 1 and not args.no_nohint:
+        j2 = Job(gx, torch, dist, dev, local_rank, rank, world, w, text_np, 0)
+        ms2, ph2, _, st2 = j2.timed(max(1, min(args.steps, 3)), 1)
+        nohint = {"value": tot_occ / (ms2 * 1e-3), "ms_per_step": ms2, "table": {"capacity": st2["table_capacity"], "grows": st2["table_grows"]},
+                  "phase_ms_per_step": ph2, "note": "expected_kmers = 0: first region upserted as a pilot, table sized once from it"}
+        j2.close()
+
+    # ---- N > 1: BASELINE configs[3] at full size, strong scaling (the config the >= 5e9 k-mers/s target is quoted on)
+    target = None
+    if world > 1 and args.target_workload != "none":
+        tw = gx.synth.CONFIGS[args.target_workload]
+        per_rank = -(-tw.n_reads // world)
+        first = rank * per_rank
+        mine = max(0, min(per_rank, tw.n_reads - first))
+        t_text = gx.synth.shard_text(tw, rank, mine, first_record=first)
+        t_occ = gx.synth.occurrences(tw, mine)
+        t_hint = expected_distinct(tw, tw.n_reads) // world
+        tj = Job(gx, torch, dist, dev, local_rank, rank, world, tw, t_text, t_hint)
+        t_ms, t_phase, t_launch, t_stats = tj.timed(max(1, args.target_steps), 1)
+        g_occ, g_distinct, g_recbytes = tj.allsum(t_occ, t_stats["distinct_kmers"], t_stats["record_bytes"])
+        target = {"workload": workload_desc(tw, 1), "scaling": "strong", "value": g_occ / (t_ms * 1e-3), "unit": "kmers/s",
+                  "ms_per_step": t_ms, "steps": max(1, args.target_steps), "warmup": 1, "kmer_occurrences_per_step": g_occ,
+                  "distinct_kmers": g_distinct, "record_bytes": g_recbytes, "exchange_rounds_per_step": tj.rounds,
+                  "phase_ms_per_step": t_phase, "table": {"capacity": t_stats["table_capacity"], "grows": t_stats["table_grows"]},
+                  "target": ">= 5e9 k-mers/s on 8 x B200 at k=55 (BASELINE.json north_star)"}
+        tj.close()
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
     cpu = None
@@ -339,15 +496,22 @@ def main():
             "config": {"workload": workload_desc(w, 1), "k": w.k, "read_len": w.read_len, "reads_per_gpu": n_reads,
                        "kmer_occurrences_per_step": tot_occ, "distinct_kmers": tot_distinct,
                        "l2": "inputs (text + hash table) larger than L2; no flush needed",
-                       "parallelism": f"hash-partitioned x{world}" if world > 1 else "single GPU"},
+                       "parallelism": f"hash-partitioned x{world}, one exchange round per 256 MiB chunk" if world > 1 else "single GPU"},
             "bases_per_sec": tot_bases / (ms_per_step * 1e-3),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches * args.steps),
             "roofline": roof, "cpu_baseline": cpu,
-            "phase_ms_per_step": {k_: v / args.steps for k_, v in phase_acc.items()},
-            "table": {"capacity": stats["table_capacity"], "grows": stats["table_grows"]},
+            "phase_ms_per_step": phase,
+            "table": table_info,
         }
+        if nohint is not None:
+            line["no_hint"] = nohint
+        if nvlink is not None:
+            line["nvlink"] = nvlink
+        if parity is not None:
+            line["parity"] = parity
+        if target is not None:
+            line["target_workload"] = target
         print(json.dumps(line), flush=True)
-    gb.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -95,10 +95,10 @@ def generate_codes(w: Workload, n_reads: int | None = None, batch: int = 1 << 20
         done += n
 
 
-def shard_text(w: Workload, rank: int, n_reads: int, batch: int = 1 << 20) -> np.ndarray:
+def shard_text(w: Workload, rank: int, n_reads: int, batch: int = 1 << 20, first_record: int | None = None) -> np.ndarray:
     """Readid text of one rank's shard of a multi-GPU workload: the genome comes from w.seed (identical on every rank), the
     rank's `n_reads` reads from an independent stream, so a rank generates only what it will push. Record ids continue
-    across ranks (rank r holds records [r*n_reads, (r+1)*n_reads))."""
+    across ranks (rank r holds records [r*n_reads, (r+1)*n_reads), or [first_record, first_record + n_reads) if given)."""
     genome = np.random.Generator(np.random.PCG64(w.seed)).integers(0, 4, size=w.genome_bp, dtype=np.uint8)
     rng = np.random.Generator(np.random.PCG64([w.seed, 7919 + rank]))
     L = w.read_len
@@ -106,7 +106,7 @@ def shard_text(w: Workload, rank: int, n_reads: int, batch: int = 1 << 20) -> np
     done = 0
     while done < n_reads:
         n = min(batch, n_reads - done)
-        first = rank * n_reads + done
+        first = (rank * n_reads if first_record is None else first_record) + done
         if not w.paired:
             starts = rng.integers(0, w.genome_bp - L + 1, size=n)
             strand = rng.integers(0, 2, size=n, dtype=np.uint8)
@@ -119,6 +119,8 @@ def shard_text(w: Workload, rank: int, n_reads: int, batch: int = 1 << 20) -> np
             right = _sample_reads(rng, genome, starts + outer - L, L, np.ones(n, np.uint8), w.error)
             parts.append(lines_from_codes(first, np.where(sw[:, None], right, left), np.where(sw[:, None], left, right)))
         done += n
+    if not parts:
+        return np.zeros(0, dtype=np.uint8)
     return parts[0] if len(parts) == 1 else np.concatenate(parts)
 
 
