@@ -12,6 +12,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -80,10 +81,14 @@ struct gx_ctx {
 
     u64* table = nullptr;
     u64 capacity = 0;
+    u64* pilot = nullptr;          // pilot table of a job without capacity hint (upsert_sources); kept for the next job
+    u64 pilot_capacity = 0;
     bool table_live = false;  // false: allocation kept from before gx_reset, content stale
     u64 grows = 0;
     u64 min_capacity = MIN_CAPACITY;
-    bool keys_estimated = false;   // the capacity already accounts for an estimate of this job's keys (hint or pilot)
+    u64 hash_mul = 1;              // table mapping: home slot = slot_of(hash * hash_mul, capacity); n_ranks except in the pilot
+    u64 chunk_distinct0 = 0;       // keys in the table when the current chunk's upserts began
+    double new_key_rate = 1.0;     // new keys per record of the previous chunk
     bool test_start_small = false; // test hook: no hint, no pilot -> the table starts at min_capacity and grows by deferral
 
     DevBuf heads, store;
@@ -95,7 +100,7 @@ struct gx_ctx {
     // build
     Arena arena;               // single GPU: the current chunk's records (reused chunk after chunk)
     u32 fixed_regions = 0;     // != 0: table regions per rank for the whole job (multi-GPU, or cfg.reserved[3])
-    DevBuf tile_prefix, deferred[2];
+    DevBuf tile_prefix, deferred[2], region_new;
     u64 upserted_records = 0;
 
     u64 global_lines = 0;
@@ -265,13 +270,7 @@ int line_error_to_status(gx_ctx* c, u64 packed) {
 }
 
 // ---- table life cycle ---------------------------------------------------------------------------------------
-// Capacity policy. The table never holds more than MAX_LOAD * capacity keys, by construction: the region upsert
-// postpones ("defers") work items once the key count reaches a limit that leaves room for everything in flight, and the
-// host grows the table and re-launches the deferred items (run_upsert). Everything else only tunes speed:
-//   * cfg.expected_kmers, if given, sizes the first allocation for TARGET_LOAD;
-//   * otherwise the first region of a chunk is upserted as a pilot: regions are uniform hash ranges, so its new keys
-//     times the number of regions estimate the chunk's new keys, and the table is sized once for that;
-//   * a table kept across gx_reset is reused as it is.
+// Capacity policy: see upsert_sources (sizing) and run_upsert_range (per-region load limit, deferral, growth).
 int alloc_table(gx_ctx* c, u64 capacity, u64** out) {
     void* p = nullptr;
     const size_t bytes = (size_t)capacity * c->ops->slot_bytes;
@@ -308,7 +307,7 @@ int ensure_table(gx_ctx* c, u64 min_capacity) {
 int grow_table_to(gx_ctx* c, u64 ncap) {
     u64* nt = nullptr;
     GX_TRY(alloc_table(c, ncap, &nt));
-    c->ops->rehash(c->table, c->capacity, nt, ncap, (u32)c->cfg.n_ranks, c->d_ctr, c->stream);
+    c->ops->rehash(c->table, c->capacity, nt, ncap, c->hash_mul, c->d_ctr, c->stream);
     GX_TRY(check_launch(c, "rehash"));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     CUDA_TRY(c, cudaFree(c->table));
@@ -341,7 +340,7 @@ int handle_spills(gx_ctx* c) {
         GX_TRY(set_spill_target(c));   // new spills (from the re-insertion itself) go to the other buffer
         GX_TRY(grow_table_to(c, c->capacity * 2));
         c->ops->insert_records((const u64*)c->spill_keys[old].p, (const unsigned short*)c->spill_meta[old].p,
-                               (const u32*)c->spill_counts[old].p, n, c->table, c->capacity, (u32)c->cfg.n_ranks, c->d_ctr, c->stream);
+                               (const u32*)c->spill_counts[old].p, n, c->table, c->capacity, c->hash_mul, c->d_ctr, c->stream);
         GX_TRY(check_launch(c, "insert_records"));
         GX_TRY(sync_counters(c));
     }
@@ -403,22 +402,24 @@ int split_chunk(gx_ctx* c, const uint8_t* d_text, size_t n, u64 n_lines, u64 chu
 }
 
 // K2: upsert regions [r0, r1) of the given record areas; grows the table and re-launches whatever the kernel deferred.
-// Leaves the stream synchronised and c->h_ctr current.
-int run_upsert_range(gx_ctx* c, const UpsertSrc* src, u32 n_src, u32 n_regions, u32 r0, u32 r1, u64 max_items);
+// `map_regions` = table regions the current mapping (c->hash_mul) spreads over the table: n_regions for the job's table,
+// 1 for the pilot table. Leaves the stream synchronised and c->h_ctr current.
+int run_upsert_range(gx_ctx* c, const UpsertSrc* src, u32 n_src, u32 n_regions, u32 r0, u32 r1, u64 max_items, u32 map_regions);
 
-int run_upsert(gx_ctx* c, const UpsertSrc* src, u32 n_src, u32 n_regions, u32 r0, u32 r1, u64 max_items) {
+int run_upsert(gx_ctx* c, const UpsertSrc* src, u32 n_src, u32 n_regions, u32 r0, u32 r1, u64 max_items, u32 map_regions) {
     // the kernel keeps the (region, source) pair descriptors of a launch in shared memory: at most UP_MAX_PAIRS of them
     u32 step = std::max<u32>(1, UP_MAX_PAIRS / n_src);
     if (const char* e = getenv("GENOMIX_GB_UPSERT_STEP")) step = std::max<u32>(1, std::min<u32>(step, (u32)atoi(e)));   // tuning
-    for (u32 r = r0; r < r1; r += step) GX_TRY(run_upsert_range(c, src, n_src, n_regions, r, std::min(r1, r + step), max_items));
+    for (u32 r = r0; r < r1; r += step) GX_TRY(run_upsert_range(c, src, n_src, n_regions, r, std::min(r1, r + step), max_items, map_regions));
     return GX_OK;
 }
 
-int run_upsert_range(gx_ctx* c, const UpsertSrc* src, u32 n_src, u32 n_regions, u32 r0, u32 r1, u64 max_items) {
+int run_upsert_range(gx_ctx* c, const UpsertSrc* src, u32 n_src, u32 n_regions, u32 r0, u32 r1, u64 max_items, u32 map_regions) {
     UpsertArgs a{};
     for (u32 s = 0; s < n_src; ++s) a.src[s] = src[s];
     a.n_src = n_src; a.r0 = r0; a.r1 = r1; a.n_regions = n_regions; a.n_ranks = (u32)c->cfg.n_ranks;
     a.ctr = c->d_ctr;
+    a.region_new = (u32*)c->region_new.p;
     const size_t n_pairs = (size_t)(r1 - r0) * n_src;
     GX_TRY(ensure(c, c->tile_prefix, (n_pairs + 1) * sizeof(u32)));
     GX_TRY(ensure(c, c->deferred[0], (size_t)max_items * sizeof(u32)));
@@ -430,16 +431,24 @@ int run_upsert_range(gx_ctx* c, const UpsertSrc* src, u32 n_src, u32 n_regions, 
     u64 n_deferred = 0;
     const u64 cta_warps = (u64)c->ops->upsert_warps;
     for (;;) {
-        a.table = c->table; a.capacity = c->capacity;
-        // Every warp in flight may add an item's worth of keys that ctr->distinct does not show yet, plus what it has not
-        // published (UP_PUBLISH), plus the item it decides on with a count that is one item old: the margin below the load
-        // limit. Small tables get fewer warps so that the margin stays a fraction of the limit.
-        const u64 limit = (u64)(MAX_LOAD * (double)c->capacity);
-        const u64 per_warp = UP_PUBLISH + 2 * UP_ITEM;
-        const u64 warps = std::max<u64>(1, std::min<u64>((u64)148 * c->ops->upsert_blocks * cta_warps, limit / (4 * per_warp)));
+        a.table = c->table; a.capacity = c->capacity; a.hash_mul = c->hash_mul;
+        // Load limit per table region: the keys the region held when the chunk began (hash-uniform share of the table's
+        // keys, plus 4 sigma) and the keys the chunk has added to it since (region_new, counted by the kernel) may not
+        // exceed MAX_LOAD of the region's slots. The kernel reads the counter before it applies an item, so what the
+        // other warps in flight add meanwhile (at most one item each) overshoots the limit: small tables get fewer
+        // warps so that this stays below half of the limit; for the 32 MB regions of a large table it is at most
+        // 0.22 (KW = 1) to 0.3 of the region, reached only if every record in flight is a new key.
+        const u64 region_slots = c->capacity / map_regions;
+        const u64 limit = (u64)(MAX_LOAD * (double)region_slots);
+        const double base_mean = (double)c->chunk_distinct0 / map_regions;
+        const u64 base = (u64)(base_mean + 4.0 * std::sqrt(base_mean)) + (c->chunk_distinct0 ? 1 : 0);
+        const u64 warps = std::max<u64>(1, std::min<u64>((u64)148 * c->ops->upsert_blocks * cta_warps, limit / (2 * UP_ITEM)));
         const unsigned grid = (unsigned)((warps + cta_warps - 1) / cta_warps);
         a.active_warps = (u32)std::min<u64>(cta_warps, warps);
-        a.hard_limit = limit - std::min<u64>(limit, (u64)grid * a.active_warps * per_warp);
+        // room == 0 with nothing in the region yet still lets the first items through (fill > room is the test)
+        a.region_room = limit > base ? limit - base : 0;
+        // regions with thousands of work items are counted through a 1-in-16 sample of their items (+-3 %)
+        a.sample_shift = max_items / std::max<u32>(1, n_regions) >= 4096 ? 4 : 0;
         a.deferred_out = (u32*)c->deferred[cur].p;
         a.deferred_in = n_deferred ? (const u32*)c->deferred[cur ^ 1].p : nullptr;
         a.n_deferred_in = (u32)n_deferred;
@@ -449,7 +458,7 @@ int run_upsert_range(gx_ctx* c, const UpsertSrc* src, u32 n_src, u32 n_regions, 
         GX_TRY(handle_spills(c));
         n_deferred = c->h_ctr->deferred_count;
         if (!n_deferred) return GX_OK;
-        // the table reached its load limit: double it and apply what was postponed
+        // a region reached its load limit: double the table and apply what was postponed
         GX_TRY(grow_table_to(c, c->capacity * 2));
         CUDA_TRY(c, cudaMemsetAsync(&c->d_ctr->deferred_count, 0, sizeof(u64), c->stream));
         cur ^= 1;
@@ -457,36 +466,82 @@ int run_upsert_range(gx_ctx* c, const UpsertSrc* src, u32 n_src, u32 n_regions, 
 }
 
 // Upsert all regions of `n_src` record areas holding `total` records: capacity policy around run_upsert.
+// Correctness never depends on the sizing below (per-region deferral + growth bound the load by construction); it decides
+// how often the table has to be rehashed:
+//   * cfg.expected_kmers, if given, sizes the first allocation for TARGET_LOAD;
+//   * else the first chunk's region 0 is upserted into a small *pilot table* whose mapping spreads that one region over
+//     all of its slots (hash_mul = n_ranks * n_regions). Regions are uniform hash ranges, so its key count times the
+//     number of regions estimates the chunk's keys; the job's table is allocated once for that and the pilot table is
+//     rehashed into it;
+//   * later chunks grow the table ahead of time when the previous chunk's new-key rate says they will not fit.
 int upsert_sources(gx_ctx* c, const UpsertSrc* src, u32 n_src, u32 n_regions, u64 total, int phase = PH_INSERT) {
     if (total == 0) return GX_OK;
     const u64 max_items = total / UP_ITEM + (u64)n_regions * n_src + 1;
     if (max_items >= 0xffffffffull) return fail(c, GX_ERR_INVALID, "chunk of %llu k-mer records is too large", (unsigned long long)total);
     const u64 distinct0 = c->table_live ? c->h_ctr->distinct : 0;
     const u64 hint = c->test_start_small ? 0 : c->cfg.expected_kmers;
+    const u64 n_ranks = (u64)c->cfg.n_ranks;
+    c->chunk_distinct0 = distinct0;
+    c->hash_mul = n_ranks;
+    GX_TRY(ensure(c, c->region_new, (size_t)SP_MAX_BUCKETS * sizeof(u32)));
+    CUDA_TRY(c, cudaMemsetAsync(c->region_new.p, 0, (size_t)SP_MAX_BUCKETS * sizeof(u32), c->stream));
+    u32 r = 0;
     if (!c->table_live) {
         u64 cap = c->min_capacity;
         if (hint) cap = std::max<u64>(cap, (u64)((double)hint / TARGET_LOAD) + 1);
-        else if (!c->test_start_small) cap = std::max<u64>(cap, n_regions >= 8 ? 4 * (total / n_regions) : (u64)((double)total / TARGET_LOAD) + 1);
-        GX_TRY(ensure_table(c, cap));
-        c->keys_estimated = hint != 0;
-    }
-    u32 r = 0;
-    const bool worst_case_fits = (double)(distinct0 + total) <= MAX_LOAD * (double)c->capacity;
-    const bool trust_hint = hint && distinct0 < hint;
-    if (!worst_case_fits && !trust_hint && !c->test_start_small && n_regions >= 8) {
-        // pilot: region 0 tells how many of this chunk's records are new keys
-        ScopedPhase ph(c, phase);
-        GX_TRY(run_upsert(c, src, n_src, n_regions, 0, 1, max_items));
-        const u64 added = c->h_ctr->distinct - distinct0;
-        const u64 expect = distinct0 + (u64)((double)added * n_regions * 1.03) + 65536;
+        else if (!c->test_start_small && n_regions < 8) cap = std::max<u64>(cap, (u64)((double)total / TARGET_LOAD) + 1);
+        if (!hint && !c->test_start_small && n_regions >= 8) {
+            // pilot: region 0 alone, in a table of its own, tells how many of this chunk's records are distinct keys
+            ScopedPhase ph(c, phase);
+            const u64 share = total / n_regions;
+            const u64 pilot_cap = std::max<u64>(65536, (u64)((double)(share + share / 8 + 4096) / MAX_LOAD) + 1);
+            u64* const kept = c->table;             // allocation kept across gx_reset (content stale), if any
+            const u64 kept_cap = c->capacity;
+            if (c->pilot && (c->pilot_capacity < pilot_cap || c->pilot_capacity > 4 * pilot_cap)) {
+                CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+                CUDA_TRY(c, cudaFree(c->pilot));
+                c->pilot = nullptr;
+            }
+            if (c->pilot) {
+                c->ops->init_table(c->pilot, c->pilot_capacity, c->stream);
+                GX_TRY(check_launch(c, "init_table"));
+            } else {
+                GX_TRY(alloc_table(c, pilot_cap, &c->pilot));
+                c->pilot_capacity = pilot_cap;
+            }
+            c->table = c->pilot; c->capacity = c->pilot_capacity; c->table_live = true;
+            c->pilot = nullptr;                     // run_upsert may replace (grow) the table it works on
+            c->hash_mul = n_ranks * n_regions;
+            c->chunk_distinct0 = 0;
+            const u64 grows0 = c->grows;
+            GX_TRY(run_upsert(c, src, n_src, n_regions, 0, 1, max_items, 1));
+            c->grows = grows0;
+            c->pilot = c->table; c->pilot_capacity = c->capacity;
+            c->table = kept; c->capacity = kept_cap; c->table_live = false;
+            c->hash_mul = n_ranks;
+            const u64 expect = (u64)((double)c->h_ctr->distinct * n_regions * 1.03) + 65536;
+            const u64 want = std::max<u64>(cap, (u64)((double)expect / TARGET_LOAD) + 1);
+            if (c->table && (c->capacity < want || c->capacity > 2 * want)) {   // a kept allocation of the wrong size
+                CUDA_TRY(c, cudaFree(c->table));
+                c->table = nullptr; c->capacity = 0;
+            }
+            GX_TRY(ensure_table(c, want));
+            c->ops->rehash(c->pilot, c->pilot_capacity, c->table, c->capacity, c->hash_mul, c->d_ctr, c->stream);   // pilot -> job table
+            GX_TRY(check_launch(c, "rehash"));
+            r = 1;
+        } else {
+            GX_TRY(ensure_table(c, cap));
+        }
+    } else if ((double)(distinct0 + total) > MAX_LOAD * (double)c->capacity && !(hint && distinct0 < hint)) {
+        // the chunk's worst case does not fit: make room for what the previous chunk's new-key rate predicts
+        const u64 expect = distinct0 + (u64)(c->new_key_rate * 1.25 * (double)total) + 65536;
         const u64 want = (u64)((double)expect / TARGET_LOAD) + 1;
         if (want > c->capacity) GX_TRY(grow_table_to(c, want));
-        c->keys_estimated = true;
-        r = 1;
     }
     ScopedPhase ph(c, phase);
-    GX_TRY(run_upsert(c, src, n_src, n_regions, r, n_regions, max_items));
+    GX_TRY(run_upsert(c, src, n_src, n_regions, r, n_regions, max_items, n_regions));
     c->upserted_records += total;
+    c->new_key_rate = (double)(c->h_ctr->distinct - distinct0) / (double)total;
     return GX_OK;
 }
 
@@ -674,7 +729,8 @@ int gx_reset(gx_ctx* c) {
     CUDA_TRY(c, cudaMemcpyAsync(c->d_ctr, c->h_ctr, sizeof z, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     c->table_live = false;  // keep the allocation; it is re-initialised on first use
-    c->keys_estimated = false;
+    c->hash_mul = (u64)c->cfg.n_ranks;
+    c->new_key_rate = 1.0;
     c->upserted_records = 0;
     c->spill_cur = 0;
     GX_TRY(set_spill_target(c));
@@ -701,11 +757,12 @@ void gx_destroy(gx_ctx* c) {
     for (auto e : c->event_pool) cudaEventDestroy(e);
     DevBuf* bufs[] = {&c->heads, &c->store, &c->text, &c->nl_pos, &c->nl_pos2, &c->desc, &c->tile_sums, &c->hslot, &c->hcount, &c->hstart,
                       &c->hperm, &c->tile_bytes, &c->tile_nodes, &c->records, &c->rec_offsets, &c->parts, &c->dense,
-                      &c->tile_prefix, &c->deferred[0], &c->deferred[1], &c->gstats};
+                      &c->tile_prefix, &c->deferred[0], &c->deferred[1], &c->region_new, &c->gstats};
     for (auto* b : bufs) release(*b);
     release_arena(c->arena);
     for (int i = 0; i < 2; ++i) { release(c->spill_keys[i]); release(c->spill_meta[i]); release(c->spill_counts[i]); }
     if (c->table) cudaFree(c->table);
+    if (c->pilot) cudaFree(c->pilot);
     if (c->d_ctr) cudaFree(c->d_ctr);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);

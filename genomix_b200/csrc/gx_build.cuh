@@ -126,7 +126,7 @@ template <int KW>
 __global__ void __launch_bounds__(256) insert_records_kernel(const u64* __restrict__ keys,
                                                              const unsigned short* __restrict__ meta,
                                                              const u32* __restrict__ counts, u64 n, u64* table, u64 capacity,
-                                                             u32 n_ranks, Counters* ctr) {
+                                                             u64 hash_mul, Counters* ctr) {
     u32 new_slots = 0;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
         u64 key[KW];
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) insert_records_kernel(const u64* __restri
         for (int j = 0; j < KW; ++j) key[j] = keys[i * KW + j];
         const u32 cnt = counts ? counts[i] : 1u;
         bool is_new;
-        if (table_upsert<KW>(table, capacity, local_hash(hash_key<KW>(key), n_ranks), key, (u64)cnt, meta[i], is_new) == capacity)
+        if (table_upsert<KW>(table, capacity, local_hash(hash_key<KW>(key), hash_mul), key, (u64)cnt, meta[i], is_new) == capacity)
             spill_record<KW>(ctr, key, meta[i], cnt);
         new_slots += is_new ? 1u : 0u;
     }
@@ -154,12 +154,12 @@ __global__ void __launch_bounds__(256) init_table_kernel(u64* __restrict__ table
     }
 }
 
-// grow: re-insert every occupied slot of the old table (count and mask carried over). Home slots are monotone in the
-// hash and both tables use the same hash, so the old table read in slot order lands in the new one in (almost)
-// slot order: the pass streams through both. A record whose probe budget runs out is spilled with its count.
+// grow: re-insert every occupied slot of the old table (count and mask carried over) under the new table's mapping
+// (`hash_mul`; the old table is only scanned). Home slots are monotone in the hash, so when both tables use the same
+// mapping the old table read in slot order lands in the new one in (almost) slot order: the pass streams through both. A record whose probe budget runs out is spilled with its count.
 template <int KW>
 __global__ void __launch_bounds__(256) rehash_kernel(const u64* __restrict__ old_table, u64 old_capacity,
-                                                     u64* __restrict__ table, u64 capacity, u32 n_ranks, Counters* ctr) {
+                                                     u64* __restrict__ table, u64 capacity, u64 hash_mul, Counters* ctr) {
     constexpr int SW = SlotTraits<KW>::WORDS;
     for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < old_capacity; s += (u64)gridDim.x * blockDim.x) {
         const u64* p = old_table + s * SW;
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) rehash_kernel(const u64* __restrict__ old
         for (int j = 0; j < KW; ++j) key[j] = p[j];
         const u64 v = p[KW];
         bool is_new;
-        if (table_upsert<KW>(table, capacity, local_hash(hash_key<KW>(key), n_ranks), key, v & COUNT_MASK, (u32)(v >> MASK_SHIFT),
+        if (table_upsert<KW>(table, capacity, local_hash(hash_key<KW>(key), hash_mul), key, v & COUNT_MASK, (u32)(v >> MASK_SHIFT),
                              is_new) == capacity) {
             // cannot happen while capacity > old occupancy; kept lossless anyway (counts above 2^32-1 are split)
             u64 left = v & COUNT_MASK;

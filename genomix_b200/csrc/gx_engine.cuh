@@ -23,8 +23,8 @@ struct EngineOps {
     void (*upsert_regions)(const UpsertArgs& a, unsigned grid, cudaStream_t st);
     void (*check_arena)(const u64* keys, const u64* seg_start, u32 n_ranks, u32 n_regions, u64* bad, cudaStream_t st);
     void (*insert_records)(const u64* keys, const unsigned short* meta, const u32* counts, u64 n, u64* table,
-                           u64 capacity, u32 n_ranks, Counters* ctr, cudaStream_t st);
-    void (*rehash)(const u64* old_table, u64 old_capacity, u64* table, u64 capacity, u32 n_ranks, Counters* ctr, cudaStream_t st);
+                           u64 capacity, u64 hash_mul, Counters* ctr, cudaStream_t st);
+    void (*rehash)(const u64* old_table, u64 old_capacity, u64* table, u64 capacity, u64 hash_mul, Counters* ctr, cudaStream_t st);
     void (*heads_count)(const void* heads, u64 n_heads, const u64* table, u64 capacity, u32 n_ranks, u64* hslot, u32* hcount,
                         Counters* ctr, cudaStream_t st);
     void (*heads_sort)(const void* heads, const u64* hslot, u64 n_heads, u64 capacity, const u32* hstart, u32* hcount,

@@ -86,7 +86,9 @@ __host__ __device__ __forceinline__ u64 mulhi64(u64 a, u64 b) {
 #endif
 }
 __host__ __device__ __forceinline__ u32 owner_of(u64 h, u32 n_ranks) { return (u32)mulhi64(h, (u64)n_ranks); }
-__host__ __device__ __forceinline__ u64 local_hash(u64 h, u32 n_ranks) { return h * (u64)n_ranks; }
+__host__ __device__ __forceinline__ u64 local_hash(u64 h, u64 n_ranks) { return h * n_ranks; }
+// (the table kernels take the multiplier as `hash_mul`: n_ranks for the job's table; n_ranks * n_regions for the pilot
+//  table of gx_api.cu, which holds region 0 only and so spreads that region's hash range over all of its slots)
 __host__ __device__ __forceinline__ u32 region_of(u64 hl, u32 n_regions) { return (u32)mulhi64(hl, (u64)n_regions); }
 __host__ __device__ __forceinline__ u64 slot_of(u64 hl, u64 capacity) { return mulhi64(hl, capacity); }
 

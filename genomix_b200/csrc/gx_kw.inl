@@ -23,12 +23,12 @@ void l_check_arena(const u64* keys, const u64* seg_start, u32 n_ranks, u32 n_reg
     check_arena_kernel<KW><<<148 * 8, 256, 0, st>>>(keys, seg_start, n_ranks, n_regions, bad);
 }
 void l_insert_records(const u64* keys, const unsigned short* meta, const u32* counts, u64 n, u64* table, u64 capacity,
-                      u32 n_ranks, Counters* ctr, cudaStream_t st) {
+                      u64 hash_mul, Counters* ctr, cudaStream_t st) {
     if (n == 0) return;
-    insert_records_kernel<KW><<<grid_for(n, 256, 148 * 8), 256, 0, st>>>(keys, meta, counts, n, table, capacity, n_ranks, ctr);
+    insert_records_kernel<KW><<<grid_for(n, 256, 148 * 8), 256, 0, st>>>(keys, meta, counts, n, table, capacity, hash_mul, ctr);
 }
-void l_rehash(const u64* old_table, u64 old_capacity, u64* table, u64 capacity, u32 n_ranks, Counters* ctr, cudaStream_t st) {
-    rehash_kernel<KW><<<grid_for(old_capacity, 256, 148 * 8), 256, 0, st>>>(old_table, old_capacity, table, capacity, n_ranks, ctr);
+void l_rehash(const u64* old_table, u64 old_capacity, u64* table, u64 capacity, u64 hash_mul, Counters* ctr, cudaStream_t st) {
+    rehash_kernel<KW><<<grid_for(old_capacity, 256, 148 * 8), 256, 0, st>>>(old_table, old_capacity, table, capacity, hash_mul, ctr);
 }
 void l_heads_count(const void* heads, u64 n_heads, const u64* table, u64 capacity, u32 n_ranks, u64* hslot, u32* hcount,
                    Counters* ctr, cudaStream_t st) {

@@ -391,9 +391,13 @@ struct UpsertArgs {
     u32 n_ranks;
     u32 active_warps;      // warps per CTA that take work (fewer for tiny tables, so that the in-flight margin stays small)
     u64* table; u64 capacity;
+    u64 hash_mul;              // home slot = slot_of(hash * hash_mul, capacity): n_ranks, or n_ranks * n_regions (pilot table)
     Counters* ctr;
     const u32* item_prefix;    // [(r1 - r0) * n_src + 1] exclusive prefix of work items per pair
-    u64 hard_limit;            // work items are deferred (not applied) once ctr->distinct exceeds this
+    u32* region_new;           // [n_regions] keys this chunk has added to each table region so far
+    u64 region_room;           // work items of a region are deferred (not applied) once region_new[region] exceeds this
+    u32 sample_shift;          // region_new is fed by every 2^sample_shift-th work item, its new keys scaled up accordingly:
+                               // one hot counter per region cannot take an atomic from every item of every warp
     u32* deferred_out;         // deferred work item ids -> ctr->deferred_count
     const u32* deferred_in;    // != nullptr: apply exactly these n_deferred_in work items
     u32 n_deferred_in;
@@ -462,12 +466,11 @@ __global__ void __launch_bounds__(UpsertCfg<KW>::THREADS, UpsertCfg<KW>::MIN_BLO
     const u32 gw = blockIdx.x * a.active_warps + warp, n_gw = gridDim.x * a.active_warps;
     u32 pair = 0;
     u32 unpublished = 0;                                 // slots this warp created and has not added to ctr->distinct yet
-    u64 next_distinct = ld_relaxed(&a.ctr->distinct);    // refreshed one item ahead, so the load never stalls the warp
 
-    // work item w -> its id t, its records and how many there are (n == 0: no such item)
+    // work item w -> its id t, its pair, its records and how many there are (n == 0: no such item)
     u64 nkey[UP_PER_LANE][KW];
     u32 nm[UP_PER_LANE];
-    u32 nn = 0, nt = 0;
+    u32 nn = 0, nt = 0, npair = 0;
     auto fetch = [&](u32 w) {
         nn = 0;
         if (w >= total) return;
@@ -488,6 +491,7 @@ __global__ void __launch_bounds__(UpsertCfg<KW>::THREADS, UpsertCfg<KW>::MIN_BLO
         const u64* keys = S.keys + first * KW;
         const unsigned short* meta = S.meta + first;
         nt = t;
+        npair = pair;
         nn = min((u32)UP_ITEM, Q.count[pair] - item_off);
 #pragma unroll
         for (int i = 0; i < UP_PER_LANE; ++i) {
@@ -504,6 +508,7 @@ __global__ void __launch_bounds__(UpsertCfg<KW>::THREADS, UpsertCfg<KW>::MIN_BLO
         u64 key[UP_PER_LANE][KW];
         u32 m[UP_PER_LANE];
         const u32 n = nn, t = nt;
+        u32* fill_p = a.region_new + (a.r0 + npair / a.n_src);   // keys this chunk has added to the item's table region
 #pragma unroll
         for (int i = 0; i < UP_PER_LANE; ++i) {
             m[i] = nm[i];
@@ -511,15 +516,11 @@ __global__ void __launch_bounds__(UpsertCfg<KW>::THREADS, UpsertCfg<KW>::MIN_BLO
             for (int j = 0; j < KW; ++j) key[i][j] = nkey[i][j];
         }
         if constexpr (PREFETCH) fetch(w + n_gw);
-        // apply the item only while the table has room for everything that all warps in flight could still add
-        // (hard_limit leaves that margin); otherwise hand it back to the host, which grows the table
-        const u64 distinct_now = next_distinct;
-        next_distinct = ld_relaxed(&a.ctr->distinct);
-        if (distinct_now > a.hard_limit) {
-            if (lane == 0) a.deferred_out[atomicAdd(&a.ctr->deferred_count, 1ull)] = t;
-            if constexpr (!PREFETCH) fetch(w + n_gw);
-            continue;
-        }
+        // The item is applied only while its table region has room: a region is a contiguous slot range that this chunk
+        // fills while the regions after it still wait, so the load limit has to hold per region, not on average. The
+        // counter load travels with the slot loads below; what the warps in flight add after it was read is the
+        // overshoot the host leaves room for (run_upsert_range).
+        const u32 fill = ld_relaxed_u32(fill_p);
 
         // ---- stage 1: home-slot snapshots of the item's records
         u64* sp[UP_PER_LANE];
@@ -527,9 +528,14 @@ __global__ void __launch_bounds__(UpsertCfg<KW>::THREADS, UpsertCfg<KW>::MIN_BLO
 #pragma unroll
         for (int i = 0; i < UP_PER_LANE; ++i) {
             if (lane + 32u * i < n) {
-                sp[i] = a.table + slot_of(local_hash(hash_key<KW>(key[i]), a.n_ranks), a.capacity) * SW;
+                sp[i] = a.table + slot_of(local_hash(hash_key<KW>(key[i]), a.hash_mul), a.capacity) * SW;
                 probe_load<KW>(sp[i], pr[i]);
             }
+        }
+        if ((u64)fill > a.region_room) {   // region full: hand the item back to the host, which grows the table
+            if (lane == 0) a.deferred_out[atomicAdd(&a.ctr->deferred_count, 1ull)] = t;
+            if constexpr (!PREFETCH) fetch(w + n_gw);
+            continue;
         }
         // ---- stage 2: fold what is there, claim what is empty
         u32 slow = 0, claim = 0, n_new = 0;   // bit i: record i of this lane
@@ -620,7 +626,7 @@ __global__ void __launch_bounds__(UpsertCfg<KW>::THREADS, UpsertCfg<KW>::MIN_BLO
                 for (int x = 0; x < KW; ++x) k2[x] = qk[j * KW + x];
                 const u32 m2 = qm[j];
                 bool is_new;
-                if (table_upsert<KW>(a.table, a.capacity, local_hash(hash_key<KW>(k2), a.n_ranks), k2, 1ull, m2, is_new) == a.capacity)
+                if (table_upsert<KW>(a.table, a.capacity, local_hash(hash_key<KW>(k2), a.hash_mul), k2, 1ull, m2, is_new) == a.capacity)
                     spill_record<KW>(a.ctr, k2, m2);
                 n_new += is_new ? 1u : 0u;
             }
@@ -628,6 +634,7 @@ __global__ void __launch_bounds__(UpsertCfg<KW>::THREADS, UpsertCfg<KW>::MIN_BLO
         }
 #pragma unroll
         for (int dlt = 16; dlt > 0; dlt >>= 1) n_new += __shfl_xor_sync(0xffffffffu, n_new, dlt);
+        if (lane == 0 && n_new && (t & ((1u << a.sample_shift) - 1u)) == 0) atomicAdd(fill_p, n_new << a.sample_shift);
         unpublished += n_new;
         if (unpublished >= UP_PUBLISH) {
             if (lane == 0) atomicAdd(&a.ctr->distinct, (u64)unpublished);

@@ -39,12 +39,13 @@ def iter_chunks(path1: str, path2: Optional[str] = None, chunk_bytes: int = 128 
     b1, b2 = bytearray(), bytearray()
     first_record = 0
     eof1 = eof2 = False
+    starved = False   # the last round produced nothing: read on even if a buffer is already chunk-sized
     while True:
-        if not eof1 and len(b1) < chunk_bytes:
+        if not eof1 and (len(b1) < chunk_bytes or starved):
             d = f1.read(chunk_bytes)
             eof1 = len(d) == 0
             b1 += d
-        if f2 is not None and not eof2 and len(b2) < chunk_bytes:
+        if f2 is not None and not eof2 and (len(b2) < chunk_bytes or starved):
             d = f2.read(chunk_bytes)
             eof2 = len(d) == 0
             b2 += d
@@ -53,12 +54,19 @@ def iter_chunks(path1: str, path2: Optional[str] = None, chunk_bytes: int = 128 
         if f2 is None:
             if n1 == 0 and final:
                 return
+            starved = n1 == 0
             if n1:
                 yield bytes(b1[:n1]), None, first_record
                 del b1[:n1]
                 first_record += (lines1 + 2) // 4
             continue
         n2, lines2 = _take_records(b2, None, eof2)
+        # one file exhausted while the other still has lines: the reference throws at this point
+        # (GenomixDriver.java:684-687); waiting for more data from the exhausted side would never end
+        if not final and ((eof1 and lines1 == 0 and lines2 > 0) or (eof2 and lines2 == 0 and lines1 > 0)):
+            from .graphbuild import GenomixError
+            raise GenomixError(-4,  # GX_ERR_FORMAT
+                               f"IOException: Fastq files {path1} and {path2} didn't have the same number of lines!")
         lines = min(lines1, lines2) if not final else max(lines1, lines2)
         if not final:
             lines = (lines // 4) * 4
@@ -66,6 +74,7 @@ def iter_chunks(path1: str, path2: Optional[str] = None, chunk_bytes: int = 128 
             n2, _ = _take_records(b2, lines, eof2)
         if lines == 0 and final:
             return
+        starved = lines == 0
         if lines:
             yield bytes(b1[:n1]), bytes(b2[:n2]), first_record   # unequal line counts at EOF surface as GX_ERR_FORMAT
             del b1[:n1]

@@ -49,6 +49,29 @@ def test_chunker_covers_every_record(tmp_path):
     assert single == fq1
 
 
+@pytest.mark.timeout(60)
+@pytest.mark.parametrize("short_first", [True, False])
+def test_chunker_unequal_pair_files_raise_like_the_reference(tmp_path, short_first):
+    """GenomixDriver.java:684-687: paired fastq files of different length are an IOException, also when the shorter one
+    ends many chunks before the longer one (this used to spin forever)."""
+    from genomix_b200 import fastq
+    from genomix_b200.graphbuild import GenomixError
+    rng = np.random.default_rng(3)
+    a, b = tmp_path / "a.fq", tmp_path / "b.fq"
+    a.write_bytes(make_fastq(rng, 2, 40))
+    b.write_bytes(make_fastq(rng, 200, 40))
+    p1, p2 = (a, b) if short_first else (b, a)
+    with pytest.raises(GenomixError) as ei:
+        for _ in fastq.iter_chunks(str(p1), str(p2), chunk_bytes=256):
+            pass
+    assert ei.value.status == -4 and "same number of lines" in str(ei.value)   # GX_ERR_FORMAT
+    # a line longer than the chunk size is read through, not waited for
+    c = tmp_path / "long.fq"
+    c.write_bytes(b"@r\n" + b"A" * 1000 + b"\n+\n" + b"I" * 1000 + b"\n")
+    assert sum(x[0].count(b"\n") for x in fastq.iter_chunks(str(c), None, chunk_bytes=256)) == 4
+    assert sum(x[0].count(b"\n") for x in fastq.iter_chunks(str(c), str(c), chunk_bytes=256)) == 4
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("paired", [False, True])
 def test_push_fastq_matches_oracle(paired, tmp_path):
