@@ -36,7 +36,8 @@ const EngineOps* engine_ops(int kw) {
 
 namespace {
 
-constexpr double MAX_LOAD = 0.75;     // the table never holds more keys than this fraction of its capacity
+constexpr double MAX_LOAD = 0.75;     // load limit of a table region while a chunk is upserted (per-region deferral)
+constexpr double HARD_LOAD = 0.90;    // the table as a whole never holds more keys than this fraction of its capacity
 constexpr double TARGET_LOAD = 0.60;  // capacity chosen for this load when the number of keys is known or estimated
 constexpr u64 MIN_CAPACITY = 1ull << 20;
 constexpr size_t DEFAULT_CHUNK = 256ull << 20;
@@ -93,7 +94,15 @@ struct gx_ctx {
 
     DevBuf heads, store;
     DevBuf text, nl_pos, nl_pos2, desc, tile_sums;
-    DevBuf hslot, hcount, hstart, hperm, tile_bytes, tile_nodes, records, rec_offsets, parts, dense;
+    DevBuf ht_key, ht_count, ht_start, hgroup, hentry, hperm, hoff, bkey, big_list;   // read-head groups (gx_finish)
+    DevBuf tile_state, records, rec_offsets, parts, dense, dense_h, big_tiles;
+    // streaming delivery of the record stream (gx_config.reserved[2] bit 0)
+    bool stream_records = false;
+    size_t slice_bytes = 64ull << 20;
+    DevBuf ring[2], slice_idx;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_written[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    u64 stream_next_node = 0, stream_next_byte = 0;
     DevBuf gstats;
     EmitArgs last_emit{};      // arguments of the last emit (dense node list etc.), reused by gx_graph_statistics
 
@@ -376,6 +385,7 @@ int split_chunk(gx_ctx* c, const uint8_t* d_text, size_t n, u64 n_lines, u64 chu
     SplitArgs a{};
     a.text = d_text; a.n_text = n;
     a.desc = (const LineDesc*)c->desc.p; a.n_lines = n_lines;
+    a.first_line = ((u64)c->cfg.rank << 48) | (c->global_lines - n_lines);
     a.k = c->k;
     a.heads = c->heads.p;
     a.store = (uint8_t*)c->store.p;
@@ -432,23 +442,30 @@ int run_upsert_range(gx_ctx* c, const UpsertSrc* src, u32 n_src, u32 n_regions, 
     const u64 cta_warps = (u64)c->ops->upsert_warps;
     for (;;) {
         a.table = c->table; a.capacity = c->capacity; a.hash_mul = c->hash_mul;
-        // Load limit per table region: the keys the region held when the chunk began (hash-uniform share of the table's
-        // keys, plus 4 sigma) and the keys the chunk has added to it since (region_new, counted by the kernel) may not
-        // exceed MAX_LOAD of the region's slots. The kernel reads the counter before it applies an item, so what the
-        // other warps in flight add meanwhile (at most one item each) overshoots the limit: small tables get fewer
-        // warps so that this stays below half of the limit; for the 32 MB regions of a large table it is at most
-        // 0.22 (KW = 1) to 0.3 of the region, reached only if every record in flight is a new key.
+        // (1) Whole table: every warp in flight may add an item's worth of keys that ctr->distinct does not show yet,
+        // plus what it has not published (UP_PUBLISH), plus the item it decides on with a count that is one item old:
+        // that margin below HARD_LOAD makes "the table never fills up" hold by construction.
+        // (2) Per table region (performance, not safety): the keys the region held when the chunk began (hash-uniform
+        // share of the table's keys, plus 4 sigma) and the keys the chunk has added since (region_new, a sampled count)
+        // should not exceed MAX_LOAD of the region's slots; see the kernel for how in-flight work is accounted.
+        // Small tables get fewer warps so that both margins stay fractions of their limits.
         const u64 region_slots = c->capacity / map_regions;
         const u64 limit = (u64)(MAX_LOAD * (double)region_slots);
+        const u64 hard = (u64)(HARD_LOAD * (double)c->capacity);
+        const u64 per_warp = UP_PUBLISH + 2 * UP_ITEM;
         const double base_mean = (double)c->chunk_distinct0 / map_regions;
         const u64 base = (u64)(base_mean + 4.0 * std::sqrt(base_mean)) + (c->chunk_distinct0 ? 1 : 0);
-        const u64 warps = std::max<u64>(1, std::min<u64>((u64)148 * c->ops->upsert_blocks * cta_warps, limit / (2 * UP_ITEM)));
+        const u64 warps = std::max<u64>(1, std::min<u64>((u64)148 * c->ops->upsert_blocks * cta_warps,
+                                                         std::min<u64>(limit / (2 * UP_ITEM), hard / (4 * per_warp))));
         const unsigned grid = (unsigned)((warps + cta_warps - 1) / cta_warps);
         a.active_warps = (u32)std::min<u64>(cta_warps, warps);
-        // room == 0 with nothing in the region yet still lets the first items through (fill > room is the test)
+        a.hard_limit = hard - std::min<u64>(hard, (u64)grid * a.active_warps * per_warp);
         a.region_room = limit > base ? limit - base : 0;
-        // regions with thousands of work items are counted through a 1-in-16 sample of their items (+-3 %)
-        a.sample_shift = max_items / std::max<u32>(1, n_regions) >= 4096 ? 4 : 0;
+        // regions with thousands of work items are counted through a sample of their items (1 in 16: +-3 %); the sample's
+        // granularity stays below 1/16 of the limit
+        a.sample_shift = 0;
+        if (max_items / std::max<u32>(1, n_regions) >= 4096)
+            while (a.sample_shift < 4 && ((u64)UP_ITEM << (a.sample_shift + 1)) <= limit / 16) ++a.sample_shift;
         a.deferred_out = (u32*)c->deferred[cur].p;
         a.deferred_in = n_deferred ? (const u32*)c->deferred[cur ^ 1].p : nullptr;
         a.n_deferred_in = (u32)n_deferred;
@@ -638,6 +655,11 @@ int push_fastq_chunk_device(gx_ctx* c, const uint8_t* d_text, size_t n_total, si
     return insert_parsed_chunk(c, d_text, n_total);
 }
 
+__global__ void gather_u64_kernel(const u64* __restrict__ src, const u64* __restrict__ idx, u64 n, u64* __restrict__ out) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[idx[i]];
+}
+
 int require_live(gx_ctx* c) {
     if (!c) return GX_ERR_INVALID;
     if (c->sticky) return c->sticky;
@@ -696,6 +718,8 @@ int gx_create(const gx_config* cfg, gx_ctx** out) {
     c->ops = engine_ops(c->kw);
     if (cfg->reserved[0]) c->chunk_bytes = (size_t)cfg->reserved[0];
     if (cfg->reserved[1]) c->min_capacity = std::max<u64>(8192, cfg->reserved[1]);
+    c->stream_records = cfg->reserved[2] & 1;           // records are serialised on demand by gx_next_records
+    if (const char* e = getenv("GENOMIX_GB_SLICE")) c->slice_bytes = std::max<size_t>(4096, (size_t)atoll(e));   // tuning / tests
     c->test_start_small = (cfg->reserved[2] >> 8) & 1;  // test hook: start at min_capacity, no pilot -> exercises deferral + growth
     c->fixed_regions = (u32)std::min<u64>(cfg->reserved[3], SP_MAX_BUCKETS);
     auto bail = [&](int code) { g_create_error = c->err; gx_destroy(c); return code; };
@@ -755,8 +779,9 @@ void gx_destroy(gx_ctx* c) {
     drain_timers(c);
     mg_destroy(c);
     for (auto e : c->event_pool) cudaEventDestroy(e);
-    DevBuf* bufs[] = {&c->heads, &c->store, &c->text, &c->nl_pos, &c->nl_pos2, &c->desc, &c->tile_sums, &c->hslot, &c->hcount, &c->hstart,
-                      &c->hperm, &c->tile_bytes, &c->tile_nodes, &c->records, &c->rec_offsets, &c->parts, &c->dense,
+    DevBuf* bufs[] = {&c->heads, &c->store, &c->text, &c->nl_pos, &c->nl_pos2, &c->desc, &c->tile_sums, &c->ht_key, &c->ht_count, &c->ht_start,
+                      &c->hgroup, &c->hentry, &c->hperm, &c->hoff, &c->bkey, &c->big_list, &c->tile_state, &c->records, &c->rec_offsets,
+                      &c->parts, &c->dense, &c->dense_h, &c->big_tiles, &c->ring[0], &c->ring[1], &c->slice_idx,
                       &c->tile_prefix, &c->deferred[0], &c->deferred[1], &c->region_new, &c->gstats};
     for (auto* b : bufs) release(*b);
     release_arena(c->arena);
@@ -765,6 +790,11 @@ void gx_destroy(gx_ctx* c) {
     if (c->pilot) cudaFree(c->pilot);
     if (c->d_ctr) cudaFree(c->d_ctr);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (c->ev_written[i]) cudaEventDestroy(c->ev_written[i]);
+        if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+    }
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -881,56 +911,66 @@ int gx_finish(gx_ctx* c) {
     if (!c->table || !c->table_live) GX_TRY(ensure_table(c, c->min_capacity));  // empty job: empty table, zero records
     const u64 cap = c->capacity;
     const u64 n_heads = c->h_ctr->head_cursor;
-    const u64 n_tiles = (cap + EM_TILE - 1) / EM_TILE;
+    const u64 distinct = c->h_ctr->distinct;
+    const u64 n_tiles = (cap + ES_TILE - 1) / ES_TILE;
+    EmitArgs a{};
+    a.table = c->table; a.capacity = cap; a.k = c->k;
     {
         ScopedPhase ph(c, PH_FINISH);
         if (n_heads) {
-            if (n_heads >= 0xffffffffull) return fail(c, GX_ERR_INVALID, "more than 2^32-1 read heads on one rank");
-            const u64 s_tiles = (cap + TS_TILE - 1) / TS_TILE;
-            GX_TRY(ensure(c, c->hslot, n_heads * sizeof(u64)));
-            GX_TRY(ensure(c, c->hcount, cap * sizeof(u32)));
-            GX_TRY(ensure(c, c->hstart, (cap + 1) * sizeof(u32)));
+            // read heads -> groups per node (gx_emit.cuh K3a); everything is sized by the number of heads
+            if (n_heads >= 0x7fffffffull) return fail(c, GX_ERR_INVALID, "more than 2^31-1 read heads on one rank");
+            u64 ht_size = 1024;
+            while (ht_size < 2 * n_heads) ht_size <<= 1;
+            const u64 s_tiles = (ht_size + TS_TILE - 1) / TS_TILE;
+            GX_TRY(ensure(c, c->ht_key, ht_size * sizeof(u64)));
+            GX_TRY(ensure(c, c->ht_count, ht_size * sizeof(u32)));
+            GX_TRY(ensure(c, c->ht_start, (ht_size + 1) * sizeof(u32)));
+            GX_TRY(ensure(c, c->hgroup, ht_size * sizeof(HeadGroup)));
+            GX_TRY(ensure(c, c->hentry, n_heads * sizeof(u32)));
             GX_TRY(ensure(c, c->hperm, n_heads * sizeof(u32)));
+            GX_TRY(ensure(c, c->hoff, n_heads * sizeof(u32)));
+            GX_TRY(ensure(c, c->bkey, n_heads * sizeof(u64)));
+            GX_TRY(ensure(c, c->big_list, (n_heads / HG_SMALL + 1) * sizeof(u32)));
             GX_TRY(ensure(c, c->tile_sums, (s_tiles + 1) * sizeof(u64)));
-            CUDA_TRY(c, cudaMemsetAsync(c->hcount.p, 0, cap * sizeof(u32), c->stream));
-            CUDA_TRY(c, cudaMemsetAsync(c->hperm.p, 0xff, n_heads * sizeof(u32), c->stream));
-            c->ops->heads_count(c->heads.p, n_heads, c->table, cap, (u32)c->cfg.n_ranks, (u64*)c->hslot.p, (u32*)c->hcount.p, c->d_ctr,
-                                c->stream);
-            GX_TRY(check_launch(c, "heads_count"));
-            tile_sum_u32_kernel<<<(unsigned)s_tiles, TS_THREADS, 0, c->stream>>>((const u32*)c->hcount.p, cap, (u64*)c->tile_sums.p);
+            CUDA_TRY(c, cudaMemsetAsync(c->ht_key.p, 0xff, ht_size * sizeof(u64), c->stream));
+            CUDA_TRY(c, cudaMemsetAsync(c->ht_count.p, 0, ht_size * sizeof(u32), c->stream));
+            CUDA_TRY(c, cudaMemsetAsync(&c->d_ctr->big_groups, 0, sizeof(u64), c->stream));
+            c->ops->heads_lookup(c->heads.p, n_heads, c->table, cap, (u32)c->cfg.n_ranks, (u64*)c->ht_key.p, (u32*)c->ht_count.p,
+                                 (u32)(ht_size - 1), (u32*)c->hentry.p, c->d_ctr, c->stream);
+            GX_TRY(check_launch(c, "heads_lookup"));
+            tile_sum_u32_kernel<<<(unsigned)s_tiles, TS_THREADS, 0, c->stream>>>((const u32*)c->ht_count.p, ht_size, (u64*)c->tile_sums.p);
             GX_TRY(check_launch(c, "tile_sum_u32"));
             scan_tile_sums_kernel<<<1, 1024, 0, c->stream>>>((u64*)c->tile_sums.p, s_tiles, &c->d_ctr->scratch[0]);
             GX_TRY(check_launch(c, "scan_tile_sums"));
-            tile_scan_u32_kernel<<<(unsigned)s_tiles, TS_THREADS, 0, c->stream>>>((const u32*)c->hcount.p, cap,
-                                                                                  (const u64*)c->tile_sums.p, (u32*)c->hstart.p);
+            tile_scan_u32_kernel<<<(unsigned)s_tiles, TS_THREADS, 0, c->stream>>>((const u32*)c->ht_count.p, ht_size,
+                                                                                  (const u64*)c->tile_sums.p, (u32*)c->ht_start.p);
             GX_TRY(check_launch(c, "tile_scan_u32"));
-            CUDA_TRY(c, cudaMemsetAsync(c->hcount.p, 0, cap * sizeof(u32), c->stream));
+            CUDA_TRY(c, cudaMemsetAsync(c->ht_count.p, 0, ht_size * sizeof(u32), c->stream));
             heads_scatter_kernel<<<(unsigned)((n_heads + 255) / 256), 256, 0, c->stream>>>(
-                (const u64*)c->hslot.p, n_heads, cap, (const u32*)c->hstart.p, (u32*)c->hcount.p, (u32*)c->hperm.p);
+                (const u32*)c->hentry.p, n_heads, (const u32*)c->ht_start.p, (u32*)c->ht_count.p, (u32*)c->hperm.p);
             GX_TRY(check_launch(c, "heads_scatter"));
-            c->ops->heads_sort(c->heads.p, (const u64*)c->hslot.p, n_heads, cap, (const u32*)c->hstart.p, (u32*)c->hcount.p,
-                               (u32*)c->hperm.p, c->d_ctr, c->stream);
-            GX_TRY(check_launch(c, "heads_sort"));
+            c->ops->heads_group(c->heads.p, (const u64*)c->ht_key.p, (u32)ht_size, (const u32*)c->ht_start.p, (const u32*)c->ht_count.p,
+                                (u32*)c->hperm.p, (u32*)c->hoff.p, (u64*)c->bkey.p, (HeadGroup*)c->hgroup.p, (u32*)c->big_list.p,
+                                c->d_ctr, c->stream);
+            GX_TRY(check_launch(c, "heads_group"));
+            ++c->launches;   // heads_group_big
+            a.heads = c->heads.p; a.hperm = (const u32*)c->hperm.p; a.hoff = (const u32*)c->hoff.p;
+            a.store = (const uint8_t*)c->store.p;
+            a.ht_key = (const u64*)c->ht_key.p; a.ht_mask = (u32)(ht_size - 1); a.group = (const HeadGroup*)c->hgroup.p;
         }
-        GX_TRY(ensure(c, c->tile_bytes, (n_tiles + 1) * sizeof(u64)));
-        GX_TRY(ensure(c, c->tile_nodes, (n_tiles + 1) * sizeof(u64)));
-    }
-    EmitArgs a{};
-    a.table = c->table; a.capacity = cap; a.k = c->k;
-    a.heads = c->heads.p;
-    a.hstart = n_heads ? (const u32*)c->hstart.p : nullptr;
-    a.hcount = n_heads ? (const u32*)c->hcount.p : nullptr;
-    a.hperm = n_heads ? (const u32*)c->hperm.p : nullptr;
-    a.store = (const uint8_t*)c->store.p;
-    a.tile_bytes = (u64*)c->tile_bytes.p; a.tile_nodes = (u64*)c->tile_nodes.p;
-    {
-        ScopedPhase ph(c, PH_FINISH);
-        c->ops->emit_size(a, c->stream);
-        GX_TRY(check_launch(c, "emit_size"));
-        scan_tile_sums_kernel<<<1, 1024, 0, c->stream>>>((u64*)c->tile_bytes.p, n_tiles, &c->d_ctr->scratch[0]);
-        GX_TRY(check_launch(c, "scan_tile_sums"));
-        scan_tile_sums_kernel<<<1, 1024, 0, c->stream>>>((u64*)c->tile_nodes.p, n_tiles, &c->d_ctr->scratch[1]);
-        GX_TRY(check_launch(c, "scan_tile_sums"));
+        // one pass over the table: record sizes, offsets, dense node list
+        GX_TRY(ensure(c, c->tile_state, (n_tiles + 1) * 2 * sizeof(u64)));
+        GX_TRY(ensure(c, c->dense, (size_t)std::max<u64>(distinct, 1) * (c->kw + 1) * sizeof(u64)));
+        GX_TRY(ensure(c, c->dense_h, (size_t)std::max<u64>(distinct, 1) * sizeof(u32)));
+        GX_TRY(ensure(c, c->rec_offsets, (size_t)(distinct + 1) * sizeof(u64)));
+        CUDA_TRY(c, cudaMemsetAsync(c->tile_state.p, 0, (n_tiles + 1) * 2 * sizeof(u64), c->stream));
+        a.tile_state = (u64*)c->tile_state.p;
+        a.tile_counter = (u32*)((u64*)c->tile_state.p + 2 * n_tiles);
+        a.totals = &c->d_ctr->scratch[0];
+        a.dense = (u64*)c->dense.p; a.dense_h = (u32*)c->dense_h.p; a.rec_offsets = (u64*)c->rec_offsets.p;
+        c->ops->emit_scan(a, c->stream);
+        GX_TRY(check_launch(c, "emit_scan"));
     }
     GX_TRY(sync_counters(c));
     if (c->h_ctr->table_overflow)
@@ -941,28 +981,32 @@ int gx_finish(gx_ctx* c) {
                                 (unsigned long long)c->h_ctr->heads_missing);
     c->record_bytes = c->h_ctr->scratch[0];
     c->n_nodes = c->h_ctr->scratch[1];
-    GX_TRY(ensure(c, c->records, (size_t)c->record_bytes + 16));
-    GX_TRY(ensure(c, c->rec_offsets, (size_t)(c->n_nodes + 1) * sizeof(u64)));
-    GX_TRY(ensure(c, c->dense, (size_t)std::max<u64>(c->n_nodes, 1) * (c->kw + 2) * sizeof(u64)));
-    a.out = (uint8_t*)c->records.p;
-    a.rec_offsets = (u64*)c->rec_offsets.p;
-    a.dense = (u64*)c->dense.p;
+    if (c->n_nodes != distinct)
+        return c->sticky = fail(c, GX_ERR_INVALID, "internal error: %llu occupied slots but %llu keys counted",
+                                (unsigned long long)c->n_nodes, (unsigned long long)distinct);
     a.n_nodes = c->n_nodes;
     {
-        // staging area: 1.5x the average bytes of EM_THREADS nodes; the rare CTA that needs more writes directly
+        // staging window per warp: 1.5x the average bytes of a tile of EW_NODES nodes; the rare tile that needs more is
+        // written window by window
         const u64 avg = c->n_nodes ? c->record_bytes / c->n_nodes + 1 : 64;
-        u64 stage = (avg * EM_THREADS * 3 / 2 + 2048 + 15) & ~15ull;
-        a.stage_bytes = (u32)std::min<u64>(std::max<u64>(stage, 8192), EM_MAX_STAGE_BYTES);
+        u64 stage = (avg * EW_NODES * 3 / 2 + 256 + 15) & ~15ull;
+        a.stage_bytes = (u32)std::min<u64>(std::max<u64>(stage, 1024), EM_MAX_STAGE_BYTES / EW_WARPS);
     }
-    {
+    // tiles whose span exceeds EW_MAX_WINDOWS windows: at most record_bytes / (EW_MAX_WINDOWS * stage_bytes) of them
+    GX_TRY(ensure(c, c->big_tiles, (size_t)(c->record_bytes / ((u64)EW_MAX_WINDOWS * a.stage_bytes) + 2) * sizeof(u64)));
+    a.big_tiles = (u64*)c->big_tiles.p;
+    a.big_tile_count = &c->d_ctr->big_tiles;
+    c->last_emit = a;
+    c->stream_next_node = c->stream_next_byte = 0;
+    if (!c->stream_records) {
+        // the whole record stream, resident in device memory
+        GX_TRY(ensure(c, c->records, (size_t)c->record_bytes + 16));
         ScopedPhase ph(c, PH_FINISH);
-        CUDA_TRY(c, cudaMemcpyAsync((u64*)c->rec_offsets.p + c->n_nodes, &c->h_ctr->scratch[0], sizeof(u64),
-                                    cudaMemcpyHostToDevice, c->stream));
-        c->ops->emit_compact(a, c->stream);
-        GX_TRY(check_launch(c, "emit_compact"));
-        c->ops->emit_serialise(a, c->stream);
-        if (c->n_nodes) GX_TRY(check_launch(c, "emit_serialise"));
-        c->last_emit = a;
+        a.out = (uint8_t*)c->records.p; a.out_base = 0; a.n_first = 0; a.n_last = c->n_nodes;
+        CUDA_TRY(c, cudaMemsetAsync(a.big_tile_count, 0, sizeof(u64), c->stream));
+        c->ops->emit_write(a, c->stream);
+        ++c->launches;   // emit_write_big
+        if (c->n_nodes) GX_TRY(check_launch(c, "emit_write"));
     }
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     drain_timers(c);
@@ -976,10 +1020,83 @@ int64_t gx_record_bytes(gx_ctx* c) { return (c && c->finished) ? (int64_t)c->rec
 int gx_records_device(gx_ctx* c, const uint8_t** dev_records, const uint64_t** dev_offsets) {
     GX_TRY(require_live(c));
     if (!c->finished) return fail(c, GX_ERR_STATE, "gx_records_device before gx_finish");
+    if (c->stream_records && dev_records)
+        return fail(c, GX_ERR_STATE, "gx_records_device: this job streams its records (gx_config.reserved[2] bit 0); use gx_next_records");
     if (dev_records) *dev_records = (const uint8_t*)c->records.p;
     if (dev_offsets) *dev_offsets = (const uint64_t*)c->rec_offsets.p;
     return GX_OK;
 }
+
+namespace {
+
+// (node index, byte offset) of the last record boundary at or below `limit`; synchronises the stream
+int record_boundary(gx_ctx* c, u64 limit, u64* node, u64* byte) {
+    upper_bound_kernel<<<1, 1, 0, c->stream>>>((const u64*)c->rec_offsets.p, 0, c->n_nodes, limit, &c->d_ctr->scratch[0]);
+    GX_TRY(check_launch(c, "upper_bound"));
+    GX_TRY(sync_counters(c));
+    *node = c->h_ctr->scratch[0];
+    *byte = c->h_ctr->scratch[1];
+    return GX_OK;
+}
+
+// Streaming delivery: records [cursor, end) are serialised slice by slice into two device buffers and copied to the
+// host while the next slice is being written, so the record stream never has to exist in device memory as a whole.
+int stream_records_to_host(gx_ctx* c, u64 node_lo, u64 cursor, u64 node_hi, u64 end, uint8_t* host_buf) {
+    if (!c->copy_stream) {
+        CUDA_TRY(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_written[i], cudaEventDisableTiming));
+            CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+        }
+    }
+    const u64 avg = c->n_nodes ? c->record_bytes / c->n_nodes + 1 : 64;
+    const u64 slice_nodes = std::max<u64>(EW_NODES, (c->slice_bytes / avg) / EW_NODES * EW_NODES);
+    // slice boundaries by node count (cheap: no search); the few slices that outgrow the buffers (large read-head sets)
+    // make them grow
+    std::vector<u64> bounds;   // byte offsets of the slice starts, from one small gather
+    std::vector<u64> nodes;
+    for (u64 n = node_lo; n < node_hi; n += slice_nodes) nodes.push_back(n);
+    nodes.push_back(node_hi);
+    bounds.resize(nodes.size());
+    bounds.front() = cursor; bounds.back() = end;
+    if (nodes.size() > 2) {
+        GX_TRY(ensure(c, c->slice_idx, nodes.size() * 2 * sizeof(u64)));
+        CUDA_TRY(c, cudaMemcpyAsync(c->slice_idx.p, nodes.data(), nodes.size() * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+        gather_u64_kernel<<<(unsigned)((nodes.size() + 255) / 256), 256, 0, c->stream>>>(
+            (const u64*)c->rec_offsets.p, (const u64*)c->slice_idx.p, nodes.size(), (u64*)c->slice_idx.p + nodes.size());
+        GX_TRY(check_launch(c, "gather_u64"));
+        CUDA_TRY(c, cudaMemcpyAsync(bounds.data(), (u64*)c->slice_idx.p + nodes.size(), nodes.size() * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+    EmitArgs a = c->last_emit;
+    for (size_t s = 0; s + 1 < nodes.size(); ++s) {
+        const int r = (int)(s & 1);
+        const u64 bytes = bounds[s + 1] - bounds[s];
+        if (s >= 2) CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_copied[r], 0));   // buffer r is free again
+        if (bytes + 16 > c->ring[r].cap) {
+            if (s >= 2) CUDA_TRY(c, cudaEventSynchronize(c->ev_copied[r]));
+            GX_TRY(ensure(c, c->ring[r], (size_t)bytes + 16));
+        }
+        a.out = (uint8_t*)c->ring[r].p; a.out_base = bounds[s]; a.n_first = nodes[s]; a.n_last = nodes[s + 1];
+        {
+            ScopedPhase ph(c, PH_FINISH);
+            CUDA_TRY(c, cudaMemsetAsync(a.big_tile_count, 0, sizeof(u64), c->stream));
+            c->ops->emit_write(a, c->stream);
+            GX_TRY(check_launch(c, "emit_write"));
+            ++c->launches;   // emit_write_big
+        }
+        CUDA_TRY(c, cudaEventRecord(c->ev_written[r], c->stream));
+        CUDA_TRY(c, cudaStreamWaitEvent(c->copy_stream, c->ev_written[r], 0));
+        CUDA_TRY(c, cudaMemcpyAsync(host_buf + (bounds[s] - cursor), c->ring[r].p, (size_t)bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+        CUDA_TRY(c, cudaEventRecord(c->ev_copied[r], c->copy_stream));
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    drain_timers(c);
+    return GX_OK;
+}
+
+}  // namespace
 
 int gx_next_records(gx_ctx* c, uint64_t* cursor, uint8_t* host_buf, size_t cap, size_t* used) {
     GX_TRY(require_live(c));
@@ -988,18 +1105,26 @@ int gx_next_records(gx_ctx* c, uint64_t* cursor, uint8_t* host_buf, size_t cap, 
     cudaSetDevice(c->cfg.device);
     *used = 0;
     if (*cursor >= c->record_bytes) return GX_OK;
-    u64 end = c->record_bytes;
+    u64 end = c->record_bytes, node_end = c->n_nodes;
     if (end - *cursor > cap) {
         // largest record boundary <= cursor + cap
-        upper_bound_kernel<<<1, 1, 0, c->stream>>>((const u64*)c->rec_offsets.p, 0, c->n_nodes, *cursor + cap,
-                                                   &c->d_ctr->scratch[0]);
-        GX_TRY(check_launch(c, "upper_bound"));
-        GX_TRY(sync_counters(c));
-        end = c->h_ctr->scratch[1];
+        GX_TRY(record_boundary(c, *cursor + cap, &node_end, &end));
         if (end <= *cursor) return fail(c, GX_ERR_BUFFER, "buffer of %zu bytes cannot hold the next record", cap);
     }
-    CUDA_TRY(c, cudaMemcpyAsync(host_buf, (const uint8_t*)c->records.p + *cursor, end - *cursor, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->stream_records) {
+        u64 node_lo = c->stream_next_node;
+        if (*cursor != c->stream_next_byte) {   // not the continuation of the previous call: find the record
+            u64 at = 0;
+            GX_TRY(record_boundary(c, *cursor, &node_lo, &at));
+            if (at != *cursor) return fail(c, GX_ERR_INVALID, "gx_next_records: cursor %llu is not a record boundary", (unsigned long long)*cursor);
+        }
+        GX_TRY(stream_records_to_host(c, node_lo, *cursor, node_end, end, host_buf));
+        c->stream_next_node = node_end;
+        c->stream_next_byte = end;
+    } else {
+        CUDA_TRY(c, cudaMemcpyAsync(host_buf, (const uint8_t*)c->records.p + *cursor, end - *cursor, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
     *used = (size_t)(end - *cursor);
     *cursor = end;
     return GX_OK;
@@ -1026,10 +1151,23 @@ int gx_next_frame(gx_ctx* c, uint64_t* cursor, uint8_t* frame, int32_t frame_siz
             if (in_slab(c->frame_byte_cursor, 8))
                 want = std::max<u64>(want, 8 + (u64)be32(&c->slab[c->frame_byte_cursor - c->slab_off]));
             want = std::min<u64>(want, c->record_bytes - c->frame_byte_cursor);
-            c->slab.resize(want);
-            CUDA_TRY(c, cudaMemcpyAsync(c->slab.data(), (const uint8_t*)c->records.p + c->frame_byte_cursor, want,
-                                        cudaMemcpyDeviceToHost, c->stream));
-            CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+            if (c->stream_records) {
+                // whole records through the streaming path; a record larger than the slab makes the slab grow
+                for (;;) {
+                    c->slab.resize(want);
+                    uint64_t cur = c->frame_byte_cursor;
+                    size_t got = 0;
+                    const int rc = gx_next_records(c, &cur, c->slab.data(), (size_t)want, &got);
+                    if (rc == GX_OK) { want = got; break; }
+                    if (rc != GX_ERR_BUFFER || want >= c->record_bytes - c->frame_byte_cursor) return rc;
+                    want = std::min<u64>(2 * want, c->record_bytes - c->frame_byte_cursor);
+                }
+            } else {
+                c->slab.resize(want);
+                CUDA_TRY(c, cudaMemcpyAsync(c->slab.data(), (const uint8_t*)c->records.p + c->frame_byte_cursor, want,
+                                            cudaMemcpyDeviceToHost, c->stream));
+                CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+            }
             c->slab_off = c->frame_byte_cursor;
             c->slab_len = want;
         }
@@ -1064,6 +1202,7 @@ int gx_partition_records(gx_ctx* c, int32_t n_parts, int32_t* host_parts) {
     GX_TRY(require_live(c));
     if (!c->finished) return fail(c, GX_ERR_STATE, "gx_partition_records before gx_finish");
     if (n_parts < 1 || !host_parts) return fail(c, GX_ERR_INVALID, "bad argument");
+    if (c->stream_records) return fail(c, GX_ERR_STATE, "gx_partition_records needs the device-resident record stream (job streams its records)");
     if (c->n_nodes == 0) return GX_OK;
     cudaSetDevice(c->cfg.device);
     GX_TRY(ensure(c, c->parts, c->n_nodes * sizeof(int)));

@@ -108,8 +108,9 @@ __device__ __forceinline__ void spill_record(Counters* ctr, const u64 (&key)[KW]
 // The ReadHeadInfo of a read whose first k-mer has canonical key `key` and direction `rev`
 // (ReadsKeyValueParserFactory.java:165-170: offset 0 unflipped, K-1 flipped; library always 0, :98-106).
 template <int KW>
-__device__ __forceinline__ void write_head(Head<KW>* heads, const LineDesc& d, int mate, const u64 (&key)[KW], bool rev, int k) {
+__device__ __forceinline__ void write_head(Head<KW>* heads, const LineDesc& d, u64 order, int mate, const u64 (&key)[KW], bool rev, int k) {
     Head<KW>& h = heads[d.head_idx[mate]];
+    h.order = order;
 #pragma unroll
     for (int i = 0; i < KW; ++i) h.key[i] = key[i];
     h.uuid = (rev ? ((u64)(k - 1) << 40) : 0ull) | ((u64)mate << 35) | d.read_id;

@@ -25,13 +25,12 @@ struct EngineOps {
     void (*insert_records)(const u64* keys, const unsigned short* meta, const u32* counts, u64 n, u64* table,
                            u64 capacity, u64 hash_mul, Counters* ctr, cudaStream_t st);
     void (*rehash)(const u64* old_table, u64 old_capacity, u64* table, u64 capacity, u64 hash_mul, Counters* ctr, cudaStream_t st);
-    void (*heads_count)(const void* heads, u64 n_heads, const u64* table, u64 capacity, u32 n_ranks, u64* hslot, u32* hcount,
-                        Counters* ctr, cudaStream_t st);
-    void (*heads_sort)(const void* heads, const u64* hslot, u64 n_heads, u64 capacity, const u32* hstart, u32* hcount,
-                       u32* hperm, Counters* ctr, cudaStream_t st);
-    void (*emit_size)(const EmitArgs& a, cudaStream_t st);
-    void (*emit_compact)(const EmitArgs& a, cudaStream_t st);
-    void (*emit_serialise)(const EmitArgs& a, cudaStream_t st);
+    void (*heads_lookup)(const void* heads, u64 n_heads, u64* table, u64 capacity, u32 n_ranks, u64* ht_key, u32* ht_count,
+                         u32 ht_mask, u32* hentry, Counters* ctr, cudaStream_t st);
+    void (*heads_group)(const void* heads, const u64* ht_key, u32 ht_size, const u32* ht_start, const u32* ht_count, u32* hperm,
+                        u32* hoff, u64* bkey, HeadGroup* group, u32* big_list, Counters* ctr, cudaStream_t st);
+    void (*emit_scan)(const EmitArgs& a, cudaStream_t st);
+    void (*emit_write)(const EmitArgs& a, cudaStream_t st);
     void (*graph_stats)(const EmitArgs& a, GraphStatsDev* out, cudaStream_t st);
     void (*route_heads)(const HeadRouteArgs& a, cudaStream_t st);
     void (*rebase_heads)(void* heads, u64 first, u64 n, u64 store_base, cudaStream_t st);

@@ -10,8 +10,8 @@
 //     type in {FF,FR,RF,RR} (EDGETYPE.java:6-9). F* lists hold Y = X[1:]+base (FF) or rc(Y) (FR);
 //     R* lists hold Y = base+X[:-1] (RR) or rc(Y) (RF). Set exactly as setEdgesForCurAndNext does
 //     (ReadsKeyValueParserFactory.java:209-233).
-//   * Table value word: bits 0..47 occurrence count (the reference's float coverage sum),
-//     bits 48..63 edge mask.
+//   * Table value word: bits 0..46 occurrence count (the reference's float coverage sum), bit 47 "has read
+//     heads" (set at finish), bits 48..63 edge mask.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -27,7 +27,8 @@ typedef unsigned int u32;
 
 static constexpr u64 EMPTY_WORD = ~0ull;           // key words of a free slot (never a canonical key)
 static constexpr u64 VAL_LOCK = ~0ull;             // value word of a slot being claimed (KW >= 3 protocol)
-static constexpr u64 COUNT_MASK = (1ull << 48) - 1;
+static constexpr u64 COUNT_MASK = (1ull << 47) - 1;  // value word bits 0..46: occurrence count
+static constexpr u64 HEADS_FLAG = 1ull << 47;        // value word bit 47: the node has read heads (set by gx_finish)
 static constexpr int MASK_SHIFT = 48;
 
 // ---------------------------------------------------------------------------------------------
@@ -48,6 +49,7 @@ template <int KW>
 struct Head {
     u64 key[KW];   // canonical first k-mer of the read (node that holds this head)
     u64 uuid;      // offset<<40 | library<<36 | mate<<35 | readId  (ReadHeadInfo.java:100-127)
+    u64 order;     // input order of the line the head comes from: rank << 48 | line number (TreeSet ties: first line wins)
     u64 this_off;  // read store offsets of the packed sequences (VKmer byte order, no header)
     u64 mate_off;
     u32 this_len;  // letters

@@ -30,27 +30,30 @@ void l_insert_records(const u64* keys, const unsigned short* meta, const u32* co
 void l_rehash(const u64* old_table, u64 old_capacity, u64* table, u64 capacity, u64 hash_mul, Counters* ctr, cudaStream_t st) {
     rehash_kernel<KW><<<grid_for(old_capacity, 256, 148 * 8), 256, 0, st>>>(old_table, old_capacity, table, capacity, hash_mul, ctr);
 }
-void l_heads_count(const void* heads, u64 n_heads, const u64* table, u64 capacity, u32 n_ranks, u64* hslot, u32* hcount,
-                   Counters* ctr, cudaStream_t st) {
+void l_heads_lookup(const void* heads, u64 n_heads, u64* table, u64 capacity, u32 n_ranks, u64* ht_key, u32* ht_count, u32 ht_mask,
+                    u32* hentry, Counters* ctr, cudaStream_t st) {
     if (n_heads == 0) return;
-    heads_count_kernel<KW><<<(unsigned)((n_heads + 255) / 256), 256, 0, st>>>(
-        reinterpret_cast<const Head<KW>*>(heads), n_heads, table, capacity, n_ranks, hslot, hcount, ctr);
+    heads_lookup_kernel<KW><<<(unsigned)((n_heads + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const Head<KW>*>(heads), n_heads, table, capacity, n_ranks, ht_key, ht_count, ht_mask, hentry, ctr);
 }
-void l_heads_sort(const void* heads, const u64* hslot, u64 n_heads, u64 capacity, const u32* hstart, u32* hcount,
-                  u32* hperm, Counters* ctr, cudaStream_t st) {
-    if (n_heads == 0) return;
-    heads_sort_kernel<KW><<<(unsigned)((n_heads + 255) / 256), 256, 0, st>>>(
-        reinterpret_cast<const Head<KW>*>(heads), hslot, n_heads, capacity, hstart, hcount, hperm, ctr);
+void l_heads_group(const void* heads, const u64* ht_key, u32 ht_size, const u32* ht_start, const u32* ht_count, u32* hperm, u32* hoff,
+                   u64* bkey, HeadGroup* group, u32* big_list, Counters* ctr, cudaStream_t st) {
+    const Head<KW>* h = reinterpret_cast<const Head<KW>*>(heads);
+    heads_group_kernel<KW><<<(ht_size + 255) / 256, 256, 0, st>>>(h, ht_key, ht_size, ht_start, ht_count, hperm, hoff, group, big_list, ctr);
+    // the (normally empty) list of large groups: a fixed grid, every CTA walks the list
+    heads_group_big_kernel<KW><<<148, HB_THREADS, 0, st>>>(h, ht_start, ht_count, hperm, hoff, bkey, group, big_list, ctr);
 }
-void l_emit_size(const EmitArgs& a, cudaStream_t st) {
-    emit_size_kernel<KW><<<(unsigned)((a.capacity + EM_TILE - 1) / EM_TILE), EM_THREADS, 0, st>>>(a);
+void l_emit_scan(const EmitArgs& a, cudaStream_t st) {
+    const u64 tiles = (a.capacity + ES_TILE - 1) / ES_TILE;   // persistent warps: tickets for tiles of ES_TILE slots
+    emit_scan_kernel<KW><<<grid_for(tiles, EW_WARPS, 148 * 8), EM_THREADS, 0, st>>>(a);
 }
-void l_emit_compact(const EmitArgs& a, cudaStream_t st) {
-    emit_compact_kernel<KW><<<(unsigned)((a.capacity + EM_TILE - 1) / EM_TILE), EM_THREADS, 0, st>>>(a);
-}
-void l_emit_serialise(const EmitArgs& a, cudaStream_t st) {
-    if (a.n_nodes == 0) return;
-    emit_serialise_kernel<KW><<<(unsigned)((a.n_nodes + EM_THREADS - 1) / EM_THREADS), EM_THREADS, a.stage_bytes, st>>>(a);
+void l_emit_write(const EmitArgs& a, cudaStream_t st) {
+    if (a.n_last <= a.n_first) return;
+    // persistent warps: every warp walks tiles of 32 nodes
+    const u64 tiles = (a.n_last - a.n_first + EW_NODES - 1) / EW_NODES;
+    emit_write_kernel<KW><<<grid_for(tiles, EW_WARPS, 148 * 8), EM_THREADS, (size_t)a.stage_bytes * EW_WARPS, st>>>(a);
+    // the (normally empty) list of tiles with a huge record: a fixed grid, every warp walks the list
+    emit_write_big_kernel<KW><<<148 * 2, EM_THREADS, (size_t)a.stage_bytes * EW_WARPS, st>>>(a);
 }
 void l_graph_stats(const EmitArgs& a, GraphStatsDev* out, cudaStream_t st) {
     if (a.n_nodes == 0) return;
@@ -65,7 +68,9 @@ void l_rebase_heads(void* heads, u64 first, u64 n, u64 store_base, cudaStream_t 
     rebase_heads_kernel<KW><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(heads, first, n, store_base);
 }
 int l_prepare() {
-    int r = (int)cudaFuncSetAttribute(emit_serialise_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, EM_MAX_STAGE_BYTES);
+    int r = (int)cudaFuncSetAttribute(emit_write_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, EM_MAX_STAGE_BYTES);
+    if (r == 0)
+        r = (int)cudaFuncSetAttribute(emit_write_big_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, EM_MAX_STAGE_BYTES);
     if (r == 0)
         r = (int)cudaFuncSetAttribute(split_place_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem<KW>));
     if (r == 0)
@@ -85,11 +90,10 @@ const EngineOps OPS = {KW,
                        l_check_arena,
                        l_insert_records,
                        l_rehash,
-                       l_heads_count,
-                       l_heads_sort,
-                       l_emit_size,
-                       l_emit_compact,
-                       l_emit_serialise,
+                       l_heads_lookup,
+                       l_heads_group,
+                       l_emit_scan,
+                       l_emit_write,
                        l_graph_stats,
                        l_route_heads,
                        l_rebase_heads,

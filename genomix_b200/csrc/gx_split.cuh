@@ -31,6 +31,7 @@ static constexpr int CURSOR_PAD = 16;           // bucket cursors live 128 B apa
 struct SplitArgs {
     const uint8_t* text; u64 n_text;
     const LineDesc* desc; u64 n_lines;
+    u64 first_line;         // rank << 48 | job-wide number of the chunk's first line (input order of read heads)
     int k;
     void* heads;
     uint8_t* store;
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(SP_THREADS, SplitBlocks<KW>::MIN) split_place_
                     if (p + 1u < npos) m |= edge_bit_next(rev, next_rev, window_letter(W, p + (u32)k + wbase));
                     if (p > 0u) m |= edge_bit_prev(rev, prev_rev, window_letter(W, p - 1u + wbase));
                     msk[j] = m;
-                    if (p == 0u) write_head<KW>(heads, a.desc[cur_line], mate, key[j], rev, k);
+                    if (p == 0u) write_head<KW>(heads, a.desc[cur_line], a.first_line + cur_line, mate, key[j], rev, k);
                 }
             }
             // direction of position pemit - 1 for the next chunk (only meaningful after a full chunk)
@@ -394,8 +395,11 @@ struct UpsertArgs {
     u64 hash_mul;              // home slot = slot_of(hash * hash_mul, capacity): n_ranks, or n_ranks * n_regions (pilot table)
     Counters* ctr;
     const u32* item_prefix;    // [(r1 - r0) * n_src + 1] exclusive prefix of work items per pair
+    u64 hard_limit;            // work items are deferred (not applied) once ctr->distinct exceeds this: with the margin the
+                               // host leaves for everything in flight, the table as a whole can never fill up
     u32* region_new;           // [n_regions] keys this chunk has added to each table region so far
-    u64 region_room;           // work items of a region are deferred (not applied) once region_new[region] exceeds this
+    u64 region_room;           // work items of a region are deferred once region_new[region], plus half of what the warps in
+                               // flight are adding at this warp's current rate, exceeds this
     u32 sample_shift;          // region_new is fed by every 2^sample_shift-th work item, its new keys scaled up accordingly:
                                // one hot counter per region cannot take an atomic from every item of every warp
     u32* deferred_out;         // deferred work item ids -> ctr->deferred_count
@@ -466,6 +470,8 @@ __global__ void __launch_bounds__(UpsertCfg<KW>::THREADS, UpsertCfg<KW>::MIN_BLO
     const u32 gw = blockIdx.x * a.active_warps + warp, n_gw = gridDim.x * a.active_warps;
     u32 pair = 0;
     u32 unpublished = 0;                                 // slots this warp created and has not added to ctr->distinct yet
+    u32 last_new = 0;                                    // new keys of this warp's previous item
+    u64 next_distinct = ld_relaxed(&a.ctr->distinct);    // refreshed one item ahead, so the load never stalls the warp
 
     // work item w -> its id t, its pair, its records and how many there are (n == 0: no such item)
     u64 nkey[UP_PER_LANE][KW];
@@ -516,10 +522,13 @@ __global__ void __launch_bounds__(UpsertCfg<KW>::THREADS, UpsertCfg<KW>::MIN_BLO
             for (int j = 0; j < KW; ++j) key[i][j] = nkey[i][j];
         }
         if constexpr (PREFETCH) fetch(w + n_gw);
-        // The item is applied only while its table region has room: a region is a contiguous slot range that this chunk
-        // fills while the regions after it still wait, so the load limit has to hold per region, not on average. The
-        // counter load travels with the slot loads below; what the warps in flight add after it was read is the
-        // overshoot the host leaves room for (run_upsert_range).
+        // The item is applied only while the table has room. (1) Hard guarantee: ctr->distinct plus everything all warps in
+        // flight can still add (the margin in hard_limit) stays below the table's capacity. (2) Per region: a region is a
+        // contiguous slot range that this chunk fills while the regions after it still wait, so the load limit has to
+        // hold per region, not on average; region_new is a sampled count, the warps in flight are assumed to find new
+        // keys at this warp's current rate. The counter loads travel with the slot loads below.
+        const u64 distinct_now = next_distinct;
+        next_distinct = ld_relaxed(&a.ctr->distinct);
         const u32 fill = ld_relaxed_u32(fill_p);
 
         // ---- stage 1: home-slot snapshots of the item's records
@@ -532,7 +541,8 @@ __global__ void __launch_bounds__(UpsertCfg<KW>::THREADS, UpsertCfg<KW>::MIN_BLO
                 probe_load<KW>(sp[i], pr[i]);
             }
         }
-        if ((u64)fill > a.region_room) {   // region full: hand the item back to the host, which grows the table
+        if (distinct_now > a.hard_limit || (u64)fill + (((u64)last_new * n_gw) >> 1) > a.region_room) {
+            // full: hand the item back to the host, which grows the table
             if (lane == 0) a.deferred_out[atomicAdd(&a.ctr->deferred_count, 1ull)] = t;
             if constexpr (!PREFETCH) fetch(w + n_gw);
             continue;
@@ -635,6 +645,7 @@ __global__ void __launch_bounds__(UpsertCfg<KW>::THREADS, UpsertCfg<KW>::MIN_BLO
 #pragma unroll
         for (int dlt = 16; dlt > 0; dlt >>= 1) n_new += __shfl_xor_sync(0xffffffffu, n_new, dlt);
         if (lane == 0 && n_new && (t & ((1u << a.sample_shift) - 1u)) == 0) atomicAdd(fill_p, n_new << a.sample_shift);
+        last_new = n_new;
         unpublished += n_new;
         if (unpublished >= UP_PUBLISH) {
             if (lane == 0) atomicAdd(&a.ctr->distinct, (u64)unpublished);

@@ -28,10 +28,11 @@ class GenomixError(RuntimeError):
 class GraphBuilder:
     def __init__(self, kmer_length: int, device: int = 0, rank: int = 0, n_ranks: int = 1,
                  expected_kmers: int = 0, chunk_bytes: int = 0, min_capacity: int = 0,
-                 start_small: bool = False, table_regions: int = 0):
+                 start_small: bool = False, table_regions: int = 0, stream_records: bool = False):
         """expected_kmers: optional hint (distinct k-mers this rank will own); chunk_bytes: internal chunk size;
         min_capacity / start_small: smallest table and "no sizing heuristics" (tests of the growth path);
-        table_regions: regions of the region-sorted build (0 = sized for L2)."""
+        table_regions: regions of the region-sorted build (0 = sized for L2); stream_records: records are serialised on
+        demand while they are copied to the host (no device-resident record stream)."""
         self._lib = _lib.load()
         cfg = GxConfig()
         cfg.abi_version = _lib.GX_ABI_VERSION
@@ -42,7 +43,7 @@ class GraphBuilder:
         cfg.expected_kmers = expected_kmers
         cfg.reserved[0] = chunk_bytes or int(os.environ.get("GENOMIX_GB_CHUNK", "0"))
         cfg.reserved[1] = min_capacity
-        cfg.reserved[2] = 256 if start_small else 0
+        cfg.reserved[2] = (256 if start_small else 0) | (1 if stream_records else 0)
         cfg.reserved[3] = table_regions or int(os.environ.get("GENOMIX_GB_REGIONS", "0"))
         self.kmer_length = kmer_length
         self._ctx = C.c_void_p()

@@ -64,9 +64,12 @@ typedef struct gx_config {
                                  * KmerPointable order, KmerPointable.java:94-107, but the Pregelix loader re-sorts, so the order
                                  * is not observable downstream; a sorted stream is not implemented -> GX_ERR_INVALID.) */
     uint64_t expected_kmers;    /* hint: distinct canonical k-mers this rank will own (0 = grow on demand) */
-    uint64_t reserved[4];       /* tuning/test knobs, 0 = default: [0] internal chunk bytes, [1] L2 fetch granularity,
-                                 * [2] low byte: build mode (0/1 direct, 2 L2-blocked), bit 8: test hook (predictor claims no new
-                                 * keys), [3] number of table regions of the blocked build */
+    uint64_t reserved[4];       /* tuning/test knobs, 0 = default: [0] internal chunk bytes (256 MiB), [1] smallest table
+                                 * capacity in slots (2^20), [2] bit 0: stream the records -- gx_finish sizes them, gx_next_records
+                                 * serialises them slice by slice while the previous slice travels to the host, so the stream never
+                                 * exists in device memory as a whole (gx_records_device / gx_partition_records unavailable);
+                                 * bit 8: test hook (no sizing heuristics: the table starts at [1] and grows by deferral),
+                                 * [3] table regions per rank of the region-sorted build (0 = regions of about 32 MB) */
 } gx_config;
 
 /* Counters of the job so far (the reference only logs wall time: GenomixDriver.java:459,467). */

@@ -344,3 +344,71 @@ def test_reset_and_small_record_batches():
         gb.finish()
         assert gx.types.canonical_records(gb.records()) == oracle_canonical(21, t2)
         assert gb.stats()["lines"] == 200
+
+
+@pytest.mark.parametrize("k,paired", [(21, False), (55, True)])
+def test_one_node_with_1e5_read_heads(k, paired):
+    """EdgeSizePressureTest shape: 10^5 reads that all start with the same k-mer -> ONE node carries 10^5 ReadHeadInfos
+    (both sets, duplicates of (readId, mate) among them). The heads are ordered by a CTA-wide sort and written one
+    thread per head, so the finish phase stays in the milliseconds; bit-exact against the C oracle."""
+    gx = _gx()
+    rng = np.random.default_rng(k)
+    comp = {65: 84, 67: 71, 71: 67, 84: 65}
+    head = bytes(rng.choice(list(b"ACGT"), size=k).tolist())
+    rc_head = bytes(comp[c] for c in reversed(head))
+    lines = []
+    n = 100_000
+    for i in range(n):
+        tail = bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(3, 12))).tolist())
+        read = head + tail if i % 3 else rc_head + tail            # both startReads and endReads of the node
+        rid = 4 * (i if i % 11 else i // 2) + 2                     # some (readId, mate) twice: TreeSet keeps one
+        line = b"%d\t%s" % (rid, read)
+        if paired:
+            line += b"\t" + bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(k + 1, k + 20))).tolist())
+        lines.append(line)
+    text = b"\n".join(lines) + b"\n"
+    with gx.GraphBuilder(k) as gb:
+        gb.push_lines(text)
+        gb.finish()
+        ms = gb.phase_ms()["finish"]
+        got = gx.types.canonical_records(gb.records())
+        heads = gb.stats()["read_heads"]
+    want = oracle_canonical_c(k, text)
+    assert got == want
+    assert heads > n // 2
+    assert ms < 100.0, f"finish phase took {ms:.1f} ms"
+
+
+@pytest.mark.parametrize("k,paired", [(31, False), (55, True), (91, False)])
+def test_streamed_records_equal_resident_records(k, paired, monkeypatch):
+    """gx_config.reserved[2] bit 0: records serialised slice by slice inside gx_next_records -- the same records as the
+    device-resident stream, the same bytes whatever the caller's buffer size; frames work on top of it. (Two builds of
+    the same input may order their records differently -- slot order depends on who wins an insertion race -- so builds
+    are compared canonically, pulls of one build byte by byte.)"""
+    gx = _gx()
+    rng = np.random.default_rng(1000 + k)
+    text = random_reads_text(rng, 4000, k + 5, k + 90, paired=paired, genome_len=20000)
+    want = oracle_canonical_c(k, text)
+    with gx.GraphBuilder(k) as gb2:
+        gb2.push_lines(text)
+        gb2.finish()
+        resident = gb2.records()
+        n_frames = len(list(gb2.iter_frames(32768)))
+    assert gx.types.canonical_records(resident) == want
+    monkeypatch.setenv("GENOMIX_GB_SLICE", "100000")   # many slices even for this small job
+    with gx.GraphBuilder(k, stream_records=True) as gb:
+        gb.push_lines(text)
+        gb.finish()
+        assert gb.record_bytes == len(resident)
+        whole = gb.records()
+        assert gx.types.canonical_records(whole) == want
+        assert gb.records() == whole
+        assert b"".join(gb.iter_record_batches(batch_bytes=1 << 16)) == whole
+        assert b"".join(gb.iter_record_batches(batch_bytes=5000)) == whole
+        with pytest.raises(gx.GenomixError):
+            gb.records_device()
+        frames = list(gb.iter_frames(32768))
+        assert len(frames) == n_frames
+        # the frames carry the same tuples in the same order as the record stream
+        recs = list(gx.types.iter_records(whole))
+        assert sum(int.from_bytes(f[-4:], "big") for f in frames) == len(recs)
