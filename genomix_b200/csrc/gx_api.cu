@@ -142,6 +142,7 @@ thread_local std::string g_create_error;
 // multi-GPU hooks, defined in gx_mg.inl
 int mg_stage_chunk(gx_ctx* c, const uint8_t* d_text, size_t n, u64 n_lines, u64 chunk_occ);
 int mg_pending(gx_ctx* c, u64* pending);
+int mg_complete(gx_ctx* c);
 int mg_reset(gx_ctx* c);
 void mg_destroy(gx_ctx* c);
 u64 mg_exchanged(gx_ctx* c);
@@ -469,6 +470,7 @@ int run_upsert_range(gx_ctx* c, const UpsertSrc* src, u32 n_src, u32 n_regions, 
         a.deferred_out = (u32*)c->deferred[cur].p;
         a.deferred_in = n_deferred ? (const u32*)c->deferred[cur ^ 1].p : nullptr;
         a.n_deferred_in = (u32)n_deferred;
+        CUDA_TRY(c, cudaMemsetAsync(&c->d_ctr->upsert_ticket, 0, sizeof(u64), c->stream));
         c->ops->upsert_regions(a, grid, c->stream);
         GX_TRY(check_launch(c, "upsert_regions"));
         GX_TRY(sync_counters(c));
@@ -494,7 +496,7 @@ int run_upsert_range(gx_ctx* c, const UpsertSrc* src, u32 n_src, u32 n_regions, 
 int upsert_sources(gx_ctx* c, const UpsertSrc* src, u32 n_src, u32 n_regions, u64 total, int phase = PH_INSERT) {
     if (total == 0) return GX_OK;
     const u64 max_items = total / UP_ITEM + (u64)n_regions * n_src + 1;
-    if (max_items >= 0xffffffffull) return fail(c, GX_ERR_INVALID, "chunk of %llu k-mer records is too large", (unsigned long long)total);
+    if (max_items >= 0xf0000000ull) return fail(c, GX_ERR_INVALID, "chunk of %llu k-mer records is too large", (unsigned long long)total);
     const u64 distinct0 = c->table_live ? c->h_ctr->distinct : 0;
     const u64 hint = c->test_start_small ? 0 : c->cfg.expected_kmers;
     const u64 n_ranks = (u64)c->cfg.n_ranks;
@@ -903,6 +905,7 @@ int gx_finish(gx_ctx* c) {
     if (c->h_ctr->error != ~0ull) return line_error_to_status(c, c->h_ctr->error);
     GX_TRY(handle_spills(c));
     if (c->cfg.n_ranks > 1) {
+        GX_TRY(mg_complete(c));   // the round that is still on the wire (local: no collective here)
         u64 pending = 0;
         GX_TRY(mg_pending(c, &pending));
         if (pending) return fail(c, GX_ERR_STATE, "gx_finish: %llu routed records not exchanged yet (call gx_mg_exchange on every rank first)",

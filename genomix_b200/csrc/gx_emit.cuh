@@ -571,7 +571,7 @@ __device__ __forceinline__ void write_node(const EmitArgs& a, u32* win, u32 win_
         const u32 bit = (u32)__ffs(rest) - 1u;
         const u32 t = bit >> 2, b = bit & 3u;
         const u32 nibble = (mask >> (4u * t)) & 0xfu;
-        if ((nibble & ((1u << b) - 1u)) == 0) w.put32be_any((u32)__popc(nibble));   // first edge of its list: the count
+        if ((nibble & ((1u << b) - 1u)) == 0) w.put32be((u32)__popc(nibble));   // first edge of its list: the count
         const bool from_rc = (t == 1u) || (t == 2u);
         const u32 base = from_rc ? 3u - b : b;
         u64 src[KW], app[KW], pre[KW], nk[KW];
@@ -582,7 +582,7 @@ __device__ __forceinline__ void write_node(const EmitArgs& a, u32* win, u32 win_
         const bool use_app = (t == 0u) || (t == 2u);
 #pragma unroll
         for (int i = 0; i < KW; ++i) nk[i] = use_app ? app[i] : pre[i];
-        w.put32be_any((u32)a.k);
+        w.put32be((u32)a.k);
         put_kmer_bytes<KW, CLIP>(w, nk, nb);
     }
     w.finish();

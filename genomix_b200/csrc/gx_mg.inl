@@ -77,6 +77,18 @@ struct MgState {
     u64 exchanged = 0;
     cudaStream_t comm_stream = nullptr;   // NVLink traffic runs here
     cudaEvent_t ev_ready = nullptr, ev_arrived = nullptr;
+    // The round whose records are on the wire: its upserts are launched by the NEXT gx_mg_exchange round (or gx_finish), so
+    // that the transfer overlaps whatever the caller does in between -- normally the split of the next chunk.
+    struct Rebase { u64 first, n, store_base; };
+    struct InFlight {
+        bool active = false;
+        Arena* arena = nullptr;             // send blocks + own records of the round (kept until the upserts are done)
+        std::vector<UpsertSrc> srcs;
+        u64 total = 0;
+        u64 recv_heads = 0, recv_store = 0, heads_at = 0, store_at = 0;
+        std::vector<Rebase> rebase;
+    } inflight;
+    std::vector<PendingTimer> comm_timers;
 };
 
 constexpr int MG_KINDS = 5;
@@ -98,7 +110,7 @@ int mg_pending(gx_ctx* c, u64* pending) {
     MgState* m = mg_of(c);
     *pending = 0;
     if (!m) return fail(c, GX_ERR_STATE, "n_ranks > 1 but gx_mg_init has not been called");
-    for (const Arena* ar : m->pending) *pending += ar->occ;
+    for (const Arena* ar : m->pending) if (ar) *pending += ar->occ;
     // heads created after the last exchange would also be lost
     if (c->h_ctr->head_cursor != m->routed_heads_upto) *pending += c->h_ctr->head_cursor - m->routed_heads_upto;
     return GX_OK;
@@ -106,10 +118,39 @@ int mg_pending(gx_ctx* c, u64* pending) {
 
 u64 mg_exchanged(gx_ctx* c) { return mg_of(c) ? mg_of(c)->exchanged : 0; }
 
+// Local (not collective): upsert the round that is on the wire -- own records and what the peers delivered -- and let the
+// received read heads join the local arrays. Leaves both streams synchronised.
+int mg_complete(gx_ctx* c) {
+    MgState* m = mg_of(c);
+    if (!m || !m->inflight.active) return GX_OK;
+    MgState::InFlight& f = m->inflight;
+    CUDA_TRY(c, cudaStreamWaitEvent(c->stream, m->ev_arrived, 0));
+    GX_TRY(upsert_sources(c, f.srcs.data(), (u32)f.srcs.size(), m->n_regions, f.total, PH_XINSERT));
+    if (f.recv_heads) {
+        CUDA_TRY(c, cudaMemcpyAsync((uint8_t*)c->heads.p + (size_t)f.heads_at * c->ops->head_bytes, m->inbox[3].p,
+                                    (size_t)f.recv_heads * c->ops->head_bytes, cudaMemcpyDeviceToDevice, c->stream));
+        if (f.recv_store)
+            CUDA_TRY(c, cudaMemcpyAsync((uint8_t*)c->store.p + f.store_at, m->inbox[4].p, (size_t)f.recv_store, cudaMemcpyDeviceToDevice, c->stream));
+        for (const MgState::Rebase& r : f.rebase) {
+            c->ops->rebase_heads(c->heads.p, r.first, r.n, r.store_base, c->stream);
+            GX_TRY(check_launch(c, "rebase_heads"));
+        }
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(m->comm_stream));  // the round's send blocks are reusable from here on
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    for (auto& t : m->comm_timers) c->timers.push_back(t);
+    m->comm_timers.clear();
+    drain_timers(c);
+    if (f.arena) m->free_arenas.push_back(f.arena);
+    f = MgState::InFlight();
+    return GX_OK;
+}
+
 void mg_destroy(gx_ctx* c) {
     MgState* m = mg_of(c);
     if (!m) return;
     if (m->comm_stream) cudaStreamSynchronize(m->comm_stream);
+    if (m->inflight.arena) { release_arena(*m->inflight.arena); delete m->inflight.arena; }
     if (m->comm) nccl_api().CommDestroy(m->comm);
     if (m->comm_stream) cudaStreamDestroy(m->comm_stream);
     if (m->ev_ready) cudaEventDestroy(m->ev_ready);
@@ -117,7 +158,7 @@ void mg_destroy(gx_ctx* c) {
     for (auto* v : {&m->send_heads, &m->send_store})
         for (auto& b : *v) release(b);
     for (auto* v : {&m->pending, &m->free_arenas})
-        for (Arena* ar : *v) { release_arena(*ar); delete ar; }
+        for (Arena* ar : *v) if (ar) { release_arena(*ar); delete ar; }
     for (void* mp : m->peer_ptr) if (mp) cudaIpcCloseMemHandle(mp);
     release(m->ptr_table); release(m->counts); release(m->round_vec); release(m->zero_seg); release(m->pub_dev); release(m->token);
     for (auto& b : m->inbox) release(b);
@@ -128,8 +169,13 @@ void mg_destroy(gx_ctx* c) {
 int mg_reset(gx_ctx* c) {
     MgState* m = mg_of(c);
     if (!m) return GX_OK;
+    if (m->comm_stream) CUDA_TRY(c, cudaStreamSynchronize(m->comm_stream));   // a round on the wire is dropped with the job
+    for (auto& t : m->comm_timers) { c->event_pool.push_back(t.a); c->event_pool.push_back(t.b); }
+    m->comm_timers.clear();
+    if (m->inflight.arena) m->free_arenas.push_back(m->inflight.arena);
+    m->inflight = MgState::InFlight();
     if (m->counts.p) CUDA_TRY(c, cudaMemsetAsync(m->counts.p, 0, (size_t)2 * m->n * sizeof(u64), c->stream));
-    for (Arena* ar : m->pending) m->free_arenas.push_back(ar);
+    for (Arena* ar : m->pending) if (ar) m->free_arenas.push_back(ar);
     m->pending.clear();
     m->routed_heads_upto = m->routed_store_upto = 0;
     m->exchanged = 0;
@@ -194,8 +240,12 @@ int gx_mg_init(gx_ctx* c, const uint8_t id_bytes[128]) {
     return GX_OK;
 }
 
-// Collective. Ships every staged chunk's records to their owners and upserts own + received records region by region, one
-// round per staged chunk (ranks with fewer chunks take part with empty blocks); read heads travel in the first round.
+// Collective. Ships every staged chunk's records to their owners, one round per staged chunk (ranks with fewer chunks take
+// part with empty blocks); read heads travel in the first round. Pipelined: a round's transfer is started and the call goes
+// on (or returns) without waiting for it; its upserts -- own and received records, region by region -- are launched by the
+// next round, the next gx_mg_exchange or gx_finish. So with one gx_mg_exchange per pushed chunk the NVLink transfer of chunk
+// i runs under the split of chunk i+1 (K1(i+1) || a2a(i) || K2(i-1)), and the send side never holds more
+// than two chunks of records.
 int gx_mg_exchange(gx_ctx* c) {
     GX_TRY(require_live(c));
     MgState* m = mg_of(c);
@@ -207,45 +257,7 @@ int gx_mg_exchange(gx_ctx* c) {
     const size_t V = (size_t)3 * n + 1;
     GX_TRY(sync_counters(c));
     GX_TRY(handle_spills(c));
-    const u64 head_cursor = c->h_ctr->head_cursor, store_cursor = c->h_ctr->store_cursor;
     ScopedPhase ph(c, PH_EXCHANGE);
-    // ---- 1. bucket the read heads created since the last exchange
-    const u64 new_heads = head_cursor - m->routed_heads_upto;
-    const u64 new_store = store_cursor - m->routed_store_upto;
-    for (int d = 0; d < n; ++d) {
-        if (d == me) continue;
-        GX_TRY(ensure(c, m->send_heads[d], (size_t)std::max<u64>(new_heads, 1) * c->ops->head_bytes));
-        // both mates of a pair reference the same two packed sequences and may go to the same owner: 2x
-        GX_TRY(ensure(c, m->send_store[d], (size_t)std::max<u64>(2 * new_store, 1)));
-    }
-    {
-        std::vector<void*> h((size_t)2 * n);
-        for (int d = 0; d < n; ++d) { h[d] = m->send_heads[d].p; h[(size_t)n + d] = m->send_store[d].p; }
-        CUDA_TRY(c, cudaMemcpyAsync(m->ptr_table.p, h.data(), h.size() * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
-        CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // h is a stack vector
-    }
-    if (new_heads) {
-        HeadRouteArgs ha{};
-        ha.heads = c->heads.p; ha.first = m->routed_heads_upto; ha.n = new_heads;
-        ha.store = (const uint8_t*)c->store.p;
-        ha.n_ranks = (u32)n; ha.rank = (u32)me;
-        ha.send_heads = (void* const*)m->ptr_table.p;
-        ha.send_store = (uint8_t* const*)((void**)m->ptr_table.p + n);
-        ha.send_head_count = (u64*)m->counts.p;
-        ha.send_store_bytes = (u64*)m->counts.p + n;
-        c->ops->route_heads(ha, c->stream);
-        GX_TRY(check_launch(c, "route_heads"));
-    }
-    std::vector<u64> head_counts((size_t)2 * n, 0);
-    CUDA_TRY(c, cudaMemcpyAsync(head_counts.data(), m->counts.p, head_counts.size() * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
-    // owner offsets of every staged arena
-    for (Arena* ar : m->pending) {
-        ar->owner_off.assign((size_t)n + 1, 0);
-        CUDA_TRY(c, cudaMemcpy2DAsync(ar->owner_off.data(), sizeof(u64), ar->seg_start.p, (size_t)R * sizeof(u64), sizeof(u64), (size_t)n + 1,
-                                      cudaMemcpyDeviceToHost, c->stream));
-    }
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-
     auto unit_bytes = [&](int kind) -> size_t {
         switch (kind) {
             case 0: return (size_t)c->kw * sizeof(u64);
@@ -255,12 +267,53 @@ int gx_mg_exchange(gx_ctx* c) {
             default: return 1;
         }
     };
-    u64 heads_base = head_cursor, store_base = store_cursor;   // where received heads / sequences are appended
     const size_t n_local_rounds = m->pending.size();
     size_t n_rounds = 1;
     for (size_t round = 0; round < n_rounds; ++round) {
+        // ---- 0. the round before this one (from this call or an earlier one): its records have arrived by now
+        GX_TRY(mg_complete(c));
         Arena* ar = round < n_local_rounds ? m->pending[round] : nullptr;
-        // ---- 2. everybody learns everybody's counts of this round
+        if (ar) m->pending[round] = nullptr;   // from here on the round owns it (mg_complete hands it back)
+        // ---- 1. first round: bucket the read heads created since the last exchange
+        std::vector<u64> head_counts((size_t)2 * n, 0);
+        const u64 head_cursor = c->h_ctr->head_cursor, store_cursor = c->h_ctr->store_cursor;   // current after mg_complete / sync_counters
+        if (round == 0) {
+            const u64 new_heads = head_cursor - m->routed_heads_upto;
+            const u64 new_store = store_cursor - m->routed_store_upto;
+            for (int d = 0; d < n; ++d) {
+                if (d == me) continue;
+                GX_TRY(ensure(c, m->send_heads[d], (size_t)std::max<u64>(new_heads, 1) * c->ops->head_bytes));
+                // both mates of a pair reference the same two packed sequences and may go to the same owner: 2x
+                GX_TRY(ensure(c, m->send_store[d], (size_t)std::max<u64>(2 * new_store, 1)));
+            }
+            std::vector<void*> h((size_t)2 * n);
+            for (int d = 0; d < n; ++d) { h[d] = m->send_heads[d].p; h[(size_t)n + d] = m->send_store[d].p; }
+            CUDA_TRY(c, cudaMemcpyAsync(m->ptr_table.p, h.data(), h.size() * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(c, cudaMemsetAsync(m->counts.p, 0, (size_t)2 * n * sizeof(u64), c->stream));
+            CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // h is a stack vector
+            if (new_heads) {
+                HeadRouteArgs ha{};
+                ha.heads = c->heads.p; ha.first = m->routed_heads_upto; ha.n = new_heads;
+                ha.store = (const uint8_t*)c->store.p;
+                ha.n_ranks = (u32)n; ha.rank = (u32)me;
+                ha.send_heads = (void* const*)m->ptr_table.p;
+                ha.send_store = (uint8_t* const*)((void**)m->ptr_table.p + n);
+                ha.send_head_count = (u64*)m->counts.p;
+                ha.send_store_bytes = (u64*)m->counts.p + n;
+                c->ops->route_heads(ha, c->stream);
+                GX_TRY(check_launch(c, "route_heads"));
+            }
+            CUDA_TRY(c, cudaMemcpyAsync(head_counts.data(), m->counts.p, head_counts.size() * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+        }
+        // owner offsets of this round's arena
+        if (ar) {
+            ar->owner_off.assign((size_t)n + 1, 0);
+            CUDA_TRY(c, cudaMemcpy2DAsync(ar->owner_off.data(), sizeof(u64), ar->seg_start.p, (size_t)R * sizeof(u64), sizeof(u64), (size_t)n + 1,
+                                          cudaMemcpyDeviceToHost, c->stream));
+        }
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        // ---- 2. everybody learns everybody's counts of this round. The collective also is the barrier that keeps a rank
+        //         from pushing into an inbox its owner is still reading: every rank enters it after its own mg_complete.
         std::vector<u64> vec(V, 0), all(V * (size_t)n);
         vec[0] = n_local_rounds;
         for (int d = 0; d < n; ++d) {
@@ -293,10 +346,10 @@ int gx_mg_exchange(gx_ctx* c) {
             for (int q = 0; q < s2; ++q) if (q != dst) off += count_kind(q, kind, dst);
             return off;
         };
-        u64 recv_kmers = 0, recv_heads = 0, recv_store = 0;
+        u64 recv_heads = 0, recv_store = 0;
         for (int s2 = 0; s2 < n; ++s2) {
             if (s2 == me) continue;
-            recv_kmers += count_kind(s2, 0, me); recv_heads += count_kind(s2, 3, me); recv_store += count_kind(s2, 4, me);
+            recv_heads += count_kind(s2, 3, me); recv_store += count_kind(s2, 4, me);
         }
         // ---- 3. inboxes. Every rank knows every rank's needs (the count matrix is global), so all ranks take the same
         //         decision about who has to (re)allocate: mappings of a growing inbox are closed everywhere, a barrier lets
@@ -357,11 +410,20 @@ int gx_mg_exchange(gx_ctx* c) {
         } else {
             for (int kind = 0; kind < MG_KINDS; ++kind) GX_TRY(ensure(c, m->inbox[kind], std::max<size_t>(need_bytes(me, kind), 1)));
         }
+        // ---- 4. room for the read heads that will arrive: reserved now, because the caller may push the next chunk (whose
+        //         heads are appended behind them) before they are copied in
+        const u64 heads_at = head_cursor, store_at = store_cursor;
         if (recv_heads) {
-            GX_TRY(ensure(c, c->heads, (size_t)(heads_base + recv_heads) * c->ops->head_bytes, (size_t)heads_base * c->ops->head_bytes, true));
-            GX_TRY(ensure(c, c->store, (size_t)(store_base + recv_store), (size_t)store_base));
+            GX_TRY(ensure(c, c->heads, (size_t)(heads_at + recv_heads) * c->ops->head_bytes, (size_t)heads_at * c->ops->head_bytes, true));
+            GX_TRY(ensure(c, c->store, (size_t)(store_at + recv_store), (size_t)store_at));
+            bump_cursors_kernel<<<1, 1, 0, c->stream>>>(c->d_ctr, recv_heads, recv_store);
+            GX_TRY(check_launch(c, "bump_cursors"));
         }
-        // ---- 4. all-to-all-v over NVLink on the communication stream. With CUDA IPC a delivery is a copy-engine push
+        if (round == 0) {   // everything up to here (local + arriving) is routed or owned
+            m->routed_heads_upto = heads_at + recv_heads;
+            m->routed_store_upto = store_at + recv_store;
+        }
+        // ---- 5. all-to-all-v over NVLink on the communication stream. With CUDA IPC a delivery is a copy-engine push
         //         straight into the peer's inbox (no SMs involved), all pushes of the round are followed by one tiny
         //         all-reduce as arrival barrier; without, one grouped ncclSend/ncclRecv exchange.
         CUDA_TRY(c, cudaEventRecord(m->ev_ready, c->stream));
@@ -399,56 +461,34 @@ int gx_mg_exchange(gx_ctx* c) {
         else NCCL_TRY(c, nccl_api().GroupEnd());
         CUDA_TRY(c, cudaEventRecord(m->ev_arrived, m->comm_stream));
         cudaEventRecord(comm_t.b, m->comm_stream);
-        c->timers.push_back(comm_t);
-        // ---- 5. own and received records, region by region
-        CUDA_TRY(c, cudaStreamWaitEvent(c->stream, m->ev_arrived, 0));
-        {
-            std::vector<UpsertSrc> srcs;
-            u64 total = 0;
-            if (ar && vec[1 + me]) {
-                srcs.push_back(UpsertSrc{(const u64*)ar->keys.p, (const unsigned short*)ar->meta.p, (const u64*)ar->seg_start.p + (size_t)me * R, 0});
-                total += vec[1 + me];
-            }
-            for (int s2 = 0; s2 < n; ++s2) {
-                if (s2 == me || !count_kind(s2, 0, me)) continue;
-                const u64 off = seg_off(s2, 0, me);
-                srcs.push_back(UpsertSrc{(const u64*)m->inbox[0].p + off * c->kw, (const unsigned short*)m->inbox[1].p + off,
-                                         (const u64*)((const uint8_t*)m->inbox[2].p + (size_t)seg_off(s2, 2, me) * unit_bytes(2)), 1});
-                total += count_kind(s2, 0, me);
-            }
-            GX_TRY(upsert_sources(c, srcs.data(), (u32)srcs.size(), R, total, PH_XINSERT));
+        m->comm_timers.push_back(comm_t);   // resolved by mg_complete, once the communication stream has been synchronised
+        // ---- 6. what mg_complete will upsert and append once the round has arrived
+        MgState::InFlight& f = m->inflight;
+        f.active = true;
+        f.arena = ar;
+        f.srcs.clear(); f.rebase.clear();
+        f.total = 0;
+        if (ar && vec[1 + me]) {
+            f.srcs.push_back(UpsertSrc{(const u64*)ar->keys.p, (const unsigned short*)ar->meta.p, (const u64*)ar->seg_start.p + (size_t)me * R, 0});
+            f.total += vec[1 + me];
         }
-        // ---- 6. received read heads and their sequences join the local arrays
-        if (recv_heads) {
-            CUDA_TRY(c, cudaMemcpyAsync((uint8_t*)c->heads.p + (size_t)heads_base * c->ops->head_bytes, m->inbox[3].p,
-                                        (size_t)recv_heads * c->ops->head_bytes, cudaMemcpyDeviceToDevice, c->stream));
-            if (recv_store)
-                CUDA_TRY(c, cudaMemcpyAsync((uint8_t*)c->store.p + store_base, m->inbox[4].p, (size_t)recv_store, cudaMemcpyDeviceToDevice, c->stream));
-            for (int p = 0; p < n; ++p) {
-                if (p == me) continue;
-                const u64 gh = count_kind(p, 3, me);
-                if (!gh) continue;
-                c->ops->rebase_heads(c->heads.p, heads_base + seg_off(p, 3, me), gh, store_base + seg_off(p, 4, me), c->stream);
-                GX_TRY(check_launch(c, "rebase_heads"));
-            }
-            bump_cursors_kernel<<<1, 1, 0, c->stream>>>(c->d_ctr, recv_heads, recv_store);
-            GX_TRY(check_launch(c, "bump_cursors"));
-            heads_base += recv_heads;
-            store_base += recv_store;
+        for (int s2 = 0; s2 < n; ++s2) {
+            if (s2 == me || !count_kind(s2, 0, me)) continue;
+            const u64 off = seg_off(s2, 0, me);
+            f.srcs.push_back(UpsertSrc{(const u64*)m->inbox[0].p + off * c->kw, (const unsigned short*)m->inbox[1].p + off,
+                                       (const u64*)((const uint8_t*)m->inbox[2].p + (size_t)seg_off(s2, 2, me) * unit_bytes(2)), 1});
+            f.total += count_kind(s2, 0, me);
         }
-        CUDA_TRY(c, cudaStreamSynchronize(m->comm_stream));  // this round's send blocks are reusable from here on
-        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-        // nobody may overwrite an inbox before its owner has finished reading it: the next round's (or exchange's) first
-        // collective is entered only after the local upserts completed, so it doubles as that barrier
+        f.recv_heads = recv_heads; f.recv_store = recv_store; f.heads_at = heads_at; f.store_at = store_at;
+        for (int p = 0; p < n; ++p) {
+            if (p == me) continue;
+            const u64 gh = count_kind(p, 3, me);
+            if (gh) f.rebase.push_back(MgState::Rebase{heads_at + seg_off(p, 3, me), gh, store_at + seg_off(p, 4, me)});
+        }
+        // the host copy of the cursors has to show the reservation before the next round / push reads it
+        if (recv_heads) GX_TRY(sync_counters(c));
     }
-    for (Arena* ar : m->pending) m->free_arenas.push_back(ar);
-    m->pending.clear();
-    CUDA_TRY(c, cudaMemsetAsync(m->counts.p, 0, (size_t)2 * n * sizeof(u64), c->stream));
-    m->routed_heads_upto = heads_base;
-    m->routed_store_upto = store_base;
-    // final barrier: a rank may reset / destroy its ctx (and with it inboxes its peers pushed into) only after all are done
-    NCCL_TRY(c, nccl_api().AllReduce(m->token.p, m->token.p, 1, ncclFloat, ncclSum, m->comm, c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    m->pending.clear();   // every staged arena went through a round: the last one is in flight, the others are free again
     return GX_OK;
 }
 

@@ -363,9 +363,12 @@ __global__ void __launch_bounds__(256) check_arena_kernel(const u64* __restrict_
 //   slow     the few queued records (about 6 % at load 0.4) are compacted into the low lanes and walk their probe
 //            sequences with the general table_upsert. Without the queue every warp would wait for the longest probe
 //            sequence among its 32 lanes, four times per item (measured: 3.7 dependent L2 round trips per record).
+// Measured on cfg2 (profiles/r02_tune_upsert.txt): 256 x 2 CTAs/SM without spills beats 256 x 3 with spills (a spilled
+// register makes the warp wait for the load that fills it); L2 prefetches of the next table region and of the next
+// ticket's records did not pay (the region is L2-resident after its first touches either way).
 #ifndef GX_UP_KW1_THREADS
 #define GX_UP_KW1_THREADS 256
-#define GX_UP_KW1_BLOCKS 3
+#define GX_UP_KW1_BLOCKS 2
 #endif
 // CTA shape per key width: what the register budget of the staged fast path allows
 template <int KW> struct UpsertCfg {
@@ -375,6 +378,10 @@ template <int KW> struct UpsertCfg {
 };
 static constexpr int UP_PER_LANE = 4;
 static constexpr int UP_ITEM = 32 * UP_PER_LANE;             // records per work item
+#ifndef GX_UP_TICKET
+#define GX_UP_TICKET 4
+#endif
+static constexpr u32 UP_TICKET = GX_UP_TICKET;               // consecutive work items per ticket
 static constexpr int UP_PUBLISH = 512;                       // a warp publishes its new-key count at the latest after this many
 static constexpr int UP_MAX_SRC = 64;                        // record areas walked by one launch (own + received from peers)
 
@@ -467,7 +474,18 @@ __global__ void __launch_bounds__(UpsertCfg<KW>::THREADS, UpsertCfg<KW>::MIN_BLO
     u64* qk = Q.qkeys[warp];
     unsigned short* qm = Q.qmeta[warp];
     const u32 total = a.deferred_in ? a.n_deferred_in : Q.prefix[n_pairs];
-    const u32 gw = blockIdx.x * a.active_warps + warp, n_gw = gridDim.x * a.active_warps;
+    const u32 n_gw = gridDim.x * a.active_warps;
+    // Work items are handed out by a ticket counter, one ticket ahead of use. A static round-robin deal lets the warps
+    // drift apart (an SM far from the L2 slices it talks to is several per cent slower, which adds up to dozens of items
+    // over a launch), and then the table regions in flight no longer fit in L2. With tickets all warps of the GPU work
+    // inside a window of about n_gw consecutive items: one region, or the seam between two.
+    // A ticket is worth UP_TICKET consecutive items: the counter is ONE address, and the L2 serialises the atomics on it
+    // (a ticket per item made the counter the pace-maker of the whole kernel).
+    auto take = [&]() {   // lane 0's copy is the ticket; it is broadcast where it is used, UP_TICKET items later
+        u32 t = 0;
+        if (lane == 0) t = (u32)atomicAdd(&a.ctr->upsert_ticket, 1ull) * UP_TICKET;
+        return t;
+    };
     u32 pair = 0;
     u32 unpublished = 0;                                 // slots this warp created and has not added to ctr->distinct yet
     u32 last_new = 0;                                    // new keys of this warp's previous item
@@ -509,8 +527,16 @@ __global__ void __launch_bounds__(UpsertCfg<KW>::THREADS, UpsertCfg<KW>::MIN_BLO
             }
         }
     };
-    fetch(gw);
-    for (u32 w = gw; w < total; w += n_gw) {
+    u32 w = __shfl_sync(0xffffffffu, take(), 0);
+    fetch(w);
+    u32 ticket = take(), w_next = 0;
+    for (; w < total; w = w_next) {
+        if ((w + 1u) % UP_TICKET) {
+            w_next = w + 1u;                                // next item of this ticket
+        } else {
+            w_next = __shfl_sync(0xffffffffu, ticket, 0);   // taken UP_TICKET items ago
+            ticket = take();                                // for the ticket after the next
+        }
         u64 key[UP_PER_LANE][KW];
         u32 m[UP_PER_LANE];
         const u32 n = nn, t = nt;
@@ -521,7 +547,7 @@ __global__ void __launch_bounds__(UpsertCfg<KW>::THREADS, UpsertCfg<KW>::MIN_BLO
 #pragma unroll
             for (int j = 0; j < KW; ++j) key[i][j] = nkey[i][j];
         }
-        if constexpr (PREFETCH) fetch(w + n_gw);
+        if constexpr (PREFETCH) fetch(w_next);
         // The item is applied only while the table has room. (1) Hard guarantee: ctr->distinct plus everything all warps in
         // flight can still add (the margin in hard_limit) stays below the table's capacity. (2) Per region: a region is a
         // contiguous slot range that this chunk fills while the regions after it still wait, so the load limit has to
@@ -544,7 +570,7 @@ __global__ void __launch_bounds__(UpsertCfg<KW>::THREADS, UpsertCfg<KW>::MIN_BLO
         if (distinct_now > a.hard_limit || (u64)fill + (((u64)last_new * n_gw) >> 1) > a.region_room) {
             // full: hand the item back to the host, which grows the table
             if (lane == 0) a.deferred_out[atomicAdd(&a.ctr->deferred_count, 1ull)] = t;
-            if constexpr (!PREFETCH) fetch(w + n_gw);
+            if constexpr (!PREFETCH) fetch(w_next);
             continue;
         }
         // ---- stage 2: fold what is there, claim what is empty
@@ -636,8 +662,13 @@ __global__ void __launch_bounds__(UpsertCfg<KW>::THREADS, UpsertCfg<KW>::MIN_BLO
                 for (int x = 0; x < KW; ++x) k2[x] = qk[j * KW + x];
                 const u32 m2 = qm[j];
                 bool is_new;
-                if (table_upsert<KW>(a.table, a.capacity, local_hash(hash_key<KW>(k2), a.hash_mul), k2, 1ull, m2, is_new) == a.capacity)
-                    spill_record<KW>(a.ctr, k2, m2);
+                u64 at;
+#ifndef GX_NO_WIDE
+                if constexpr (KW <= 2) at = table_upsert_wide<KW>(a.table, a.capacity, local_hash(hash_key<KW>(k2), a.hash_mul), k2, 1ull, m2, is_new);
+                else
+#endif
+                at = table_upsert<KW>(a.table, a.capacity, local_hash(hash_key<KW>(k2), a.hash_mul), k2, 1ull, m2, is_new);
+                if (at == a.capacity) spill_record<KW>(a.ctr, k2, m2);
                 n_new += is_new ? 1u : 0u;
             }
             __syncwarp();
@@ -651,7 +682,7 @@ __global__ void __launch_bounds__(UpsertCfg<KW>::THREADS, UpsertCfg<KW>::MIN_BLO
             if (lane == 0) atomicAdd(&a.ctr->distinct, (u64)unpublished);
             unpublished = 0;
         }
-        if constexpr (!PREFETCH) fetch(w + n_gw);
+        if constexpr (!PREFETCH) fetch(w_next);
     }
     if (lane == 0 && unpublished) atomicAdd(&a.ctr->distinct, (u64)unpublished);
 }

@@ -156,6 +156,52 @@ __device__ __forceinline__ u64 table_upsert(u64* __restrict__ table, u64 capacit
     return capacity;  // probe budget exhausted
 }
 
+// table_upsert for the records the staged fast path of the region upsert could not place (home slot taken by another
+// key): the same probe sequence, but PW consecutive slots are loaded per round trip and examined in registers, because
+// what these records pay for is L2 latency per probe, not bytes. KW <= 2.
+template <int KW>
+__device__ __forceinline__ u64 table_upsert_wide(u64* __restrict__ table, u64 capacity, u64 hl, const u64 (&key)[KW], u64 add,
+                                                 u32 mask, bool& is_new) {
+    static_assert(KW <= 2, "CAS-on-key protocols only");
+    constexpr int SW = SlotTraits<KW>::WORDS;
+    constexpr int PW = KW == 1 ? 4 : 2;   // 64 bytes per round trip
+    u64 slot = slot_of(hl, capacity);
+    is_new = false;
+    for (u64 budget = PROBE_BUDGET; budget; --budget) {
+        u64 w[PW][KW + 1];
+#pragma unroll
+        for (int j = 0; j < PW; ++j) {
+            const u64 sj = slot + j < capacity ? slot + j : slot + j - capacity;   // wraps around the end of the table
+            if constexpr (KW == 1) ld_relaxed_v2(table + sj * SW, w[j][0], w[j][1]);
+            else { u64 pad; ld_relaxed_v4(table + sj * SW, w[j][0], w[j][1], w[j][2], pad); }
+        }
+#pragma unroll
+        for (int j = 0; j < PW; ++j) {
+            const u64 sj = slot + j < capacity ? slot + j : slot + j - capacity;
+            u64* s = table + sj * SW;
+            bool eq = true, empty = true;
+#pragma unroll
+            for (int i = 0; i < KW; ++i) { eq = eq && w[j][i] == key[i]; empty = empty && w[j][i] == EMPTY_WORD; }
+            u64 seen = w[j][KW];
+            if (empty) {
+                u64 o0, o1;
+                if constexpr (KW == 1) {
+                    if (cas128(s, EMPTY_WORD, 0ull, key[0], add | ((u64)mask << MASK_SHIFT), o0, o1)) { is_new = true; return sj; }
+                    eq = o0 == key[0]; seen = o1;          // lost the slot: to the same key, or to another one
+                } else {
+                    if (cas128(s, EMPTY_WORD, EMPTY_WORD, key[0], key[1], o0, o1)) { is_new = true; eq = true; }
+                    else eq = o0 == key[0] && o1 == key[1];
+                    seen = 0;
+                }
+            }
+            if (eq) { fold_value(s + KW, add, mask, seen); return sj; }
+        }
+        slot += PW;
+        if (slot >= capacity) slot -= capacity;
+    }
+    return capacity;  // probe budget exhausted
+}
+
 // Find an existing key (after all inserts are complete). Returns capacity if absent.
 template <int KW>
 __device__ __forceinline__ u64 table_find(const u64* __restrict__ table, u64 capacity, u64 hl, const u64 (&key)[KW]) {
