@@ -172,15 +172,20 @@ def line_aligned_chunks(text_np, chunk_bytes):
 class Job:
     """One workload resident on this rank's GPU plus the GraphBuilder that builds it."""
 
-    def __init__(self, gx, torch, dist, dev, local_rank, rank, world, w, text_np, hint, uid=None, chunk_bytes=256 << 20):
+    def __init__(self, gx, torch, dist, dev, local_rank, rank, world, w, text_np, hint, uid=None, chunk_bytes=256 << 20,
+                 stream_records=False, share=None):
         self.torch, self.dist, self.world, self.dev = torch, dist, world, dev
         self.w = w
-        self.host_text = torch.from_numpy(text_np).pin_memory()
-        self.dev_text = self.host_text.to(dev, non_blocking=False)
-        self.gb = gx.GraphBuilder(w.k, device=local_rank, rank=rank, n_ranks=world, expected_kmers=hint, chunk_bytes=chunk_bytes)
+        if share is not None:   # same texts as another job (no second copy)
+            self.host_text, self.dev_text = share.host_text, share.dev_text
+        else:
+            self.host_text = torch.from_numpy(text_np).pin_memory()
+            self.dev_text = self.host_text.to(dev, non_blocking=False)
+        self.gb = gx.GraphBuilder(w.k, device=local_rank, rank=rank, n_ranks=world, expected_kmers=hint, chunk_bytes=chunk_bytes,
+                                  stream_records=stream_records)
         self.stream = torch.cuda.current_stream(dev)
         self.gb.set_stream(self.stream.cuda_stream)
-        self.chunks = line_aligned_chunks(text_np, chunk_bytes) if world > 1 else [(0, int(text_np.size))]
+        self.chunks = line_aligned_chunks(text_np, chunk_bytes) if (world > 1 or stream_records) else [(0, int(text_np.size))]
         self.rounds = len(self.chunks)
         if world > 1:
             uid = torch.zeros(128, dtype=torch.uint8)
@@ -211,12 +216,13 @@ class Job:
         import ctypes as C
         gb = self.gb
         gb.reset()
-        for i in range(self.rounds):
+        if self.world == 1:
+            gb.push_lines(self.host_text)   # the library cuts it into chunks and double-buffers the H2D copies
+        for i in range(self.rounds if self.world > 1 else 0):
             if i < len(self.chunks):
                 off, ln = self.chunks[i]
                 gb.push_lines(self.host_text[off:off + ln])
-            if self.world > 1:
-                gb.mg_exchange()
+            gb.mg_exchange()
         gb.finish()
         n = gb.record_bytes
         cursor, used, pos = C.c_uint64(0), C.c_size_t(0), 0
@@ -424,23 +430,31 @@ def main():
     # ---- e2e through the host API: pinned text in, whole record stream out
     e2e = None
     if not args.no_e2e:
+        # the call a user makes: host text in, records out, through a builder that streams its records (serialised slice by
+        # slice while the previous slice travels to the host) and takes the text in 64 MiB chunks (H2D of chunk i+1 under
+        # the build of chunk i)
         rec_bytes = gb.record_bytes
+        ejob = Job(gx, torch, dist, dev, local_rank, rank, world, w, text_np, hint, chunk_bytes=64 << 20, stream_records=True, share=job)
         out_host = torch.empty(max(rec_bytes, 1) + (1 << 20), dtype=torch.uint8).pin_memory()
-        job.step_host(out_host)
-        job.barrier()
+        ejob.step_host(out_host)
+        ejob.barrier()
         t0 = time.perf_counter()
         e_steps = max(1, min(args.steps, 3))
         d2h = 0
         for _ in range(e_steps):
-            d2h = job.step_host(out_host)
-        job.barrier()
+            d2h = ejob.step_host(out_host)
+        ejob.barrier()
         dt = time.perf_counter() - t0
+        e_phase = ejob.gb.phase_ms()
+        ejob.gb.close()
         if world > 1:
             t = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": tot_occ * e_steps / dt, "unit": "kmers/s", "h2d_bytes_per_step": int(job.host_text.numel()),
-               "d2h_bytes_per_step": int(d2h), "steps": e_steps, "timing": "wall clock between synchronises"}
+               "d2h_bytes_per_step": int(d2h), "steps": e_steps, "timing": "wall clock between synchronises",
+               "ms_per_step": dt / e_steps * 1e3, "last_step_phase_ms": e_phase,
+               "mode": "64 MiB text chunks double-buffered over PCIe; records streamed (gx_config.reserved[2] bit 0)"}
         del out_host
     job_rounds = job.rounds
     table_info = {"capacity": stats["table_capacity"], "grows": stats["table_grows"], "expected_kmers_hint": hint,

@@ -7,14 +7,15 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GENOMIX_GB_LIB") or os.path.join(_HERE, "libgenomix_gb.so")  # env: tuning variants only
 
-GX_ABI_VERSION = 1
+GX_ABI_VERSION = 2
 
 # every symbol include/genomix_gb.h declares (tests check that the .so exports each one)
 EXPORTS = [
     "gx_abi_version", "gx_create", "gx_destroy", "gx_reset", "gx_last_error", "gx_get_stats",
     "gx_push_lines", "gx_push_lines_device", "gx_push_fastq", "gx_finish",
     "gx_num_nodes", "gx_record_bytes", "gx_next_records", "gx_records_device", "gx_next_frame",
-    "gx_partition_records", "gx_write_sequence_file", "gx_graph_statistics", "gx_mg_unique_id", "gx_mg_init", "gx_mg_exchange",
+    "gx_partition_records", "gx_write_sequence_file", "gx_graph_statistics", "gx_coverage_histogram", "gx_coverage_cutoff",
+    "gx_mg_unique_id", "gx_mg_init", "gx_mg_exchange",
     "gx_phase_ms", "gx_kernel_launches", "gx_set_stream",
 ]
 
@@ -52,6 +53,11 @@ class GxGraphStats(C.Structure):
         ("unflipped_read_ids", C.c_uint64), ("flipped_read_ids", C.c_uint64), ("self_edges", C.c_uint64 * 4),
         ("path_nodes", C.c_uint64), ("tips_forward", C.c_uint64), ("tips_reverse", C.c_uint64), ("tips_both", C.c_uint64),
         ("tips_one", C.c_uint64),
+        ("kmer_length_total", C.c_uint64), ("kmer_length_max", C.c_uint64),
+        ("nodes_with_dir", C.c_uint64 * 2), ("coverage_with_dir_total", C.c_uint64 * 2), ("coverage_with_dir_max", C.c_uint64 * 2),
+        ("seed_nodes", C.c_uint64), ("seed_score_total", C.c_uint64), ("seed_score_max", C.c_uint64),
+        ("seed_nodes_with_dir", C.c_uint64 * 2), ("seed_score_with_dir_total", C.c_uint64 * 2),
+        ("seed_score_with_dir_max", C.c_uint64 * 2),
     ]
 
     def as_dict(self):

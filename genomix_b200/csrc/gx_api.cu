@@ -93,7 +93,7 @@ struct gx_ctx {
     bool test_start_small = false; // test hook: no hint, no pilot -> the table starts at min_capacity and grows by deferral
 
     DevBuf heads, store;
-    DevBuf text, nl_pos, nl_pos2, desc, tile_sums;
+    DevBuf text, text2, nl_pos, nl_pos2, desc, tile_sums;
     DevBuf ht_key, ht_count, ht_start, hgroup, hentry, hperm, hoff, bkey, big_list;   // read-head groups (gx_finish)
     DevBuf tile_state, records, rec_offsets, parts, dense, dense_h, big_tiles;
     // streaming delivery of the record stream (gx_config.reserved[2] bit 0)
@@ -102,6 +102,7 @@ struct gx_ctx {
     DevBuf ring[2], slice_idx;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_written[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    cudaEvent_t ev_text_ready[2] = {nullptr, nullptr}, ev_text_free[2] = {nullptr, nullptr};   // double-buffered gx_push_lines
     u64 stream_next_node = 0, stream_next_byte = 0;
     DevBuf gstats;
     EmitArgs last_emit{};      // arguments of the last emit (dense node list etc.), reused by gx_graph_statistics
@@ -225,15 +226,18 @@ struct ScopedPhase {
     }
 };
 
-// resolve finished timers (call after a stream synchronise)
+// resolve finished timers (call after a stream synchronise); timers of work still running on another stream stay pending
 void drain_timers(gx_ctx* c) {
+    size_t kept = 0;
     for (auto& t : c->timers) {
+        if (cudaEventQuery(t.b) == cudaErrorNotReady) { c->timers[kept++] = t; continue; }
         float ms = 0;
         if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) c->phase_ms[t.phase] += ms;
         c->event_pool.push_back(t.a);
         c->event_pool.push_back(t.b);
     }
-    c->timers.clear();
+    c->timers.resize(kept);
+    cudaGetLastError();   // cudaErrorNotReady is not an error here
 }
 
 int sync_counters(gx_ctx* c) {
@@ -662,6 +666,17 @@ __global__ void gather_u64_kernel(const u64* __restrict__ src, const u64* __rest
     if (i < n) out[i] = src[idx[i]];
 }
 
+int make_copy_stream(gx_ctx* c) {
+    CUDA_TRY(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_written[i], cudaEventDisableTiming));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_text_ready[i], cudaEventDisableTiming));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_text_free[i], cudaEventDisableTiming));
+    }
+    return GX_OK;
+}
+
 int require_live(gx_ctx* c) {
     if (!c) return GX_ERR_INVALID;
     if (c->sticky) return c->sticky;
@@ -781,7 +796,7 @@ void gx_destroy(gx_ctx* c) {
     drain_timers(c);
     mg_destroy(c);
     for (auto e : c->event_pool) cudaEventDestroy(e);
-    DevBuf* bufs[] = {&c->heads, &c->store, &c->text, &c->nl_pos, &c->nl_pos2, &c->desc, &c->tile_sums, &c->ht_key, &c->ht_count, &c->ht_start,
+    DevBuf* bufs[] = {&c->heads, &c->store, &c->text, &c->text2, &c->nl_pos, &c->nl_pos2, &c->desc, &c->tile_sums, &c->ht_key, &c->ht_count, &c->ht_start,
                       &c->hgroup, &c->hentry, &c->hperm, &c->hoff, &c->bkey, &c->big_list, &c->tile_state, &c->records, &c->rec_offsets,
                       &c->parts, &c->dense, &c->dense_h, &c->big_tiles, &c->ring[0], &c->ring[1], &c->slice_idx,
                       &c->tile_prefix, &c->deferred[0], &c->deferred[1], &c->region_new, &c->gstats};
@@ -796,6 +811,8 @@ void gx_destroy(gx_ctx* c) {
     for (int i = 0; i < 2; ++i) {
         if (c->ev_written[i]) cudaEventDestroy(c->ev_written[i]);
         if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+        if (c->ev_text_ready[i]) cudaEventDestroy(c->ev_text_ready[i]);
+        if (c->ev_text_free[i]) cudaEventDestroy(c->ev_text_free[i]);
     }
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -851,8 +868,9 @@ int gx_push_lines(gx_ctx* c, const uint8_t* host_text, size_t n_bytes) {
     if (c->finished) return fail(c, GX_ERR_STATE, "gx_push_lines after gx_finish (call gx_reset first)");
     if (!host_text && n_bytes) return fail(c, GX_ERR_INVALID, "null text");
     cudaSetDevice(c->cfg.device);
-    size_t pos = 0;
-    while (pos < n_bytes) {
+    // whole lines per chunk
+    std::vector<std::pair<size_t, size_t>> chunks;
+    for (size_t pos = 0; pos < n_bytes;) {
         size_t len = std::min(c->chunk_bytes, n_bytes - pos);
         if (pos + len < n_bytes) {
             const void* nl = memrchr(host_text + pos, '\n', len);
@@ -862,15 +880,35 @@ int gx_push_lines(gx_ctx* c, const uint8_t* host_text, size_t n_bytes) {
                 len = fwd ? (size_t)((const uint8_t*)fwd - (host_text + pos) + 1) : n_bytes - pos;
             }
         }
-        // the previous chunk's kernels still read c->text: the stream orders the copy after them
-        GX_TRY(ensure(c, c->text, len));
-        {
-            ScopedPhase ph(c, PH_H2D);
-            CUDA_TRY(c, cudaMemcpyAsync(c->text.p, host_text + pos, len, cudaMemcpyHostToDevice, c->stream));
-        }
-        GX_TRY(push_chunk_device(c, (const uint8_t*)c->text.p, len));
+        chunks.emplace_back(pos, len);
         pos += len;
     }
+    if (chunks.empty()) return GX_OK;
+    // Two text buffers: chunk i+1 travels to the device on the copy stream while chunk i is parsed, split and upserted.
+    if (!c->copy_stream) GX_TRY(make_copy_stream(c));
+    DevBuf* buf[2] = {&c->text, &c->text2};
+    auto start_copy = [&](size_t i) -> int {
+        const int b = (int)(i & 1);
+        GX_TRY(ensure(c, *buf[b], chunks[i].second));
+        if (i >= 2) CUDA_TRY(c, cudaStreamWaitEvent(c->copy_stream, c->ev_text_free[b], 0));   // chunk i-2 is done with the buffer
+        PendingTimer t{PH_H2D, get_event(c), get_event(c)};
+        cudaEventRecord(t.a, c->copy_stream);
+        CUDA_TRY(c, cudaMemcpyAsync(buf[b]->p, host_text + chunks[i].first, chunks[i].second, cudaMemcpyHostToDevice, c->copy_stream));
+        cudaEventRecord(t.b, c->copy_stream);
+        c->timers.push_back(t);
+        CUDA_TRY(c, cudaEventRecord(c->ev_text_ready[b], c->copy_stream));
+        return GX_OK;
+    };
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));   // kernels of an earlier push may still read the text buffers
+    GX_TRY(start_copy(0));
+    for (size_t i = 0; i < chunks.size(); ++i) {
+        const int b = (int)(i & 1);
+        if (i + 1 < chunks.size()) GX_TRY(start_copy(i + 1));
+        CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_text_ready[b], 0));
+        GX_TRY(push_chunk_device(c, (const uint8_t*)buf[b]->p, chunks[i].second));
+        CUDA_TRY(c, cudaEventRecord(c->ev_text_free[b], c->stream));
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     drain_timers(c);
     return GX_OK;
@@ -1045,13 +1083,7 @@ int record_boundary(gx_ctx* c, u64 limit, u64* node, u64* byte) {
 // Streaming delivery: records [cursor, end) are serialised slice by slice into two device buffers and copied to the
 // host while the next slice is being written, so the record stream never has to exist in device memory as a whole.
 int stream_records_to_host(gx_ctx* c, u64 node_lo, u64 cursor, u64 node_hi, u64 end, uint8_t* host_buf) {
-    if (!c->copy_stream) {
-        CUDA_TRY(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
-            CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_written[i], cudaEventDisableTiming));
-            CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
-        }
-    }
+    if (!c->copy_stream) GX_TRY(make_copy_stream(c));
     const u64 avg = c->n_nodes ? c->record_bytes / c->n_nodes + 1 : 64;
     const u64 slice_nodes = std::max<u64>(EW_NODES, (c->slice_bytes / avg) / EW_NODES * EW_NODES);
     // slice boundaries by node count (cheap: no search); the few slices that outgrow the buffers (large read-head sets)
@@ -1302,6 +1334,81 @@ int gx_graph_statistics(gx_ctx* c, gx_graph_stats* out) {
     if (c->n_nodes) GX_TRY(check_launch(c, "graph_stats"));
     CUDA_TRY(c, cudaMemcpyAsync(out, c->gstats.p, sizeof(GraphStatsDev), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return GX_OK;
+}
+
+int gx_coverage_histogram(gx_ctx* c, uint64_t* host_bins, uint64_t n_bins) {
+    GX_TRY(require_live(c));
+    if (!c->finished) return fail(c, GX_ERR_STATE, "gx_coverage_histogram before gx_finish");
+    if (!host_bins || n_bins == 0) return fail(c, GX_ERR_INVALID, "bad argument");
+    cudaSetDevice(c->cfg.device);
+    GX_TRY(ensure(c, c->gstats, std::max<size_t>(sizeof(GraphStatsDev), (size_t)n_bins * sizeof(u64))));
+    CUDA_TRY(c, cudaMemsetAsync(c->gstats.p, 0, (size_t)n_bins * sizeof(u64), c->stream));
+    c->ops->coverage_histogram(c->last_emit, (u64*)c->gstats.p, n_bins, c->stream);
+    if (c->n_nodes) GX_TRY(check_launch(c, "coverage_histogram"));
+    CUDA_TRY(c, cudaMemcpyAsync(host_bins, c->gstats.p, (size_t)n_bins * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return GX_OK;
+}
+
+// FittingMixture.fittingMixture (genomix-driver/.../mixture/model/FittingMixture.java:92-216) on the coverage histogram:
+// `data` there holds one entry per node; every node of a bin behaves identically, so the sums run over bins weighted by
+// their node counts. Densities as in commons-math3: Exponential(mean).density(x) = exp(-x/mean)/mean for x >= 0,
+// Normal(mean, sd).density(x) = exp(-(x-mean)^2 / (2 sd^2)) / (sd sqrt(2 pi)).
+int gx_coverage_cutoff(gx_ctx* c, int32_t iterations, int64_t* cutoff, double* exp_mean, double* normal_mean, double* normal_std) {
+    GX_TRY(require_live(c));
+    if (!c->finished) return fail(c, GX_ERR_STATE, "gx_coverage_cutoff before gx_finish");
+    if (!cutoff || iterations < 0) return fail(c, GX_ERR_INVALID, "bad argument");
+    gx_graph_stats gs;
+    GX_TRY(gx_graph_statistics(c, &gs));
+    const u64 max_cov = gs.coverage_max;
+    if (max_cov == 0 || gs.nodes == 0) return fail(c, GX_ERR_STATE, "IllegalStateException: No information for coverage!");
+    if (max_cov >= (1ull << 26)) return fail(c, GX_ERR_INVALID, "coverage histogram of %llu bins is too large", (unsigned long long)max_cov);
+    std::vector<uint64_t> bins(max_cov + 1);
+    GX_TRY(gx_coverage_histogram(c, bins.data(), max_cov + 1));
+    std::vector<double> xs, ws;   // distinct coverage values and their node counts
+    for (u64 v = 0; v <= max_cov; ++v)
+        if (bins[v]) { xs.push_back((double)v); ws.push_back((double)bins[v]); }
+    const size_t n = xs.size();
+    auto exp_density = [](double mean, double x) { return x < 0 ? 0.0 : std::exp(-x / mean) / mean; };
+    auto normal_density = [](double mean, double sd, double x) {
+        const double z = (x - mean) / sd;
+        return std::exp(-0.5 * z * z) / (sd * std::sqrt(2.0 * M_PI));
+    };
+    double e_mean = 5, n_mean = 20, n_sd = 5, p_exp = 0.5, p_norm = 0.5;   // initial guess (:97-109)
+    std::vector<double> m_exp(n), m_norm(n);
+    double exp_sum = 0, norm_sum = 0;
+    auto expectation = [&]() {   // :118-140 / :166-189
+        for (size_t i = 0; i < n; ++i) {
+            double a = exp_density(e_mean, xs[i]) * p_exp, b = normal_density(n_mean, n_sd, xs[i]) * p_norm;
+            if (a == 0) a = 0.000000001;
+            if (b == 0) b = 0.000000001;
+            m_exp[i] = a / (a + b);
+            m_norm[i] = b / (a + b);
+        }
+        exp_sum = norm_sum = 0;
+        for (size_t i = 0; i < n; ++i) { exp_sum += ws[i] * m_exp[i]; norm_sum += ws[i] * m_norm[i]; }
+        p_exp = exp_sum / (exp_sum + norm_sum);
+        p_norm = norm_sum / (exp_sum + norm_sum);
+    };
+    expectation();
+    for (int it = 0; it < iterations; ++it) {   // maximisation (:144-164)
+        double em = 0, nm = 0, nv = 0;
+        for (size_t i = 0; i < n; ++i) { em += ws[i] * m_exp[i] * xs[i]; nm += ws[i] * m_norm[i] * xs[i]; }
+        e_mean = em / exp_sum;
+        n_mean = nm / norm_sum;
+        for (size_t i = 0; i < n; ++i) nv += ws[i] * m_norm[i] * (xs[i] - n_mean) * (xs[i] - n_mean);
+        n_sd = std::sqrt(nv / norm_sum);
+        if (n_sd == 0) n_sd = 0.000000001f;
+        expectation();
+    }
+    *cutoff = 0;   // :208-215
+    for (double cov = 1; cov < (double)max_cov; cov += 1) {
+        if (p_exp * exp_density(e_mean, cov) < p_norm * normal_density(n_mean, n_sd, cov)) { *cutoff = (int64_t)cov; break; }
+    }
+    if (exp_mean) *exp_mean = e_mean;
+    if (normal_mean) *normal_mean = n_mean;
+    if (normal_std) *normal_std = n_sd;
     return GX_OK;
 }
 

@@ -806,7 +806,13 @@ __global__ void __launch_bounds__(EM_THREADS) emit_write_big_kernel(EmitArgs a) 
 struct GraphStatsDev {
     u64 nodes, degree_total, degree_max, degree_bins[17], coverage_total, coverage_max, coverage_bins[257];
     u64 unflipped, flipped, self_edges[4], path_nodes, tips_forward, tips_reverse, tips_both, tips_one;
+    // GraphStatistics.java:87-119: kmerLength, <x>-with-FORWARD / -with-REVERSE (nodes with degree(dir) != 0), scaffoldSeedScore
+    u64 kmer_length_total, kmer_length_max;
+    u64 nodes_with_dir[2], coverage_with_dir_total[2], coverage_with_dir_max[2];
+    u64 seed_nodes, seed_score_total, seed_score_max;
+    u64 seed_nodes_with_dir[2], seed_score_with_dir_total[2], seed_score_with_dir_max[2];
 };
+static constexpr u64 GS_COVERAGE_WINDOW = 1000;   // COVERAGE_DIST_MEAN 0 +- COVERAGE_DIST_STD 1000 (GraphStatistics.java:75-76)
 
 template <int KW>
 __global__ void __launch_bounds__(256) graph_stats_kernel(EmitArgs a, GraphStatsDev* __restrict__ out) {
@@ -818,6 +824,8 @@ __global__ void __launch_bounds__(256) graph_stats_kernel(EmitArgs a, GraphStats
     __syncthreads();
     u64 deg_tot = 0, cov_tot = 0, unfl = 0, fl = 0, path = 0, tf = 0, tr = 0, tb = 0, to = 0, nodes = 0;
     u64 deg_max = 0, cov_max = 0, self[4] = {0, 0, 0, 0};
+    u64 wd_nodes[2] = {0, 0}, wd_cov[2] = {0, 0}, wd_cov_max[2] = {0, 0};
+    u64 seed_n = 0, seed_tot = 0, seed_max = 0, wd_seed_n[2] = {0, 0}, wd_seed_tot[2] = {0, 0}, wd_seed_max[2] = {0, 0};
     for (u64 n = (u64)blockIdx.x * 256 + threadIdx.x; n < a.n_nodes; n += (u64)gridDim.x * 256) {
         const u64* d = a.dense + n * DW;
         u64 key[KW];
@@ -849,9 +857,22 @@ __global__ void __launch_bounds__(256) graph_stats_kernel(EmitArgs a, GraphStats
             else key_prepend<KW>(key, a.k, b, nk);
             if (key_eq<KW>(nk, key)) ++self[t];
         }
+        u64 n_heads = 0;
         if (val & HEADS_FLAG) {
             const HeadGroup g = a.group[a.dense_h[n]];
             unfl += g.nu; fl += g.nf;
+            n_heads = (u64)g.nu + g.nf;
+        }
+        // calculateSeedScore (Node.java:859-862): kmer length * read heads, counted for coverage within the window
+        const u64 seed = (u64)a.k * n_heads;
+        const bool in_window = cov <= GS_COVERAGE_WINDOW;
+        if (in_window) { ++seed_n; seed_tot += seed; seed_max = max(seed_max, seed); }
+        const u32 dir_deg[2] = {out_deg, in_deg};   // DIR.FORWARD = {FF, FR}, DIR.REVERSE = {RF, RR}
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+            if (dir_deg[d] == 0) continue;
+            ++wd_nodes[d]; wd_cov[d] += cov; wd_cov_max[d] = max(wd_cov_max[d], cov);
+            if (in_window) { ++wd_seed_n[d]; wd_seed_tot[d] += seed; wd_seed_max[d] = max(wd_seed_max[d], seed); }
         }
     }
     // block reductions, then one atomic per counter and CTA
@@ -862,6 +883,28 @@ __global__ void __launch_bounds__(256) graph_stats_kernel(EmitArgs a, GraphStats
     for (int t = 0; t < 4; ++t) r_self[t] = block_reduce_sum<256>(self[t]);
     atomicMax(&out->degree_max, deg_max);
     atomicMax(&out->coverage_max, cov_max);
+    atomicMax(&out->seed_score_max, seed_max);
+    for (int d = 0; d < 2; ++d) {
+        atomicMax(&out->coverage_with_dir_max[d], wd_cov_max[d]);
+        atomicMax(&out->seed_score_with_dir_max[d], wd_seed_max[d]);
+    }
+    {
+        const u64 r_sn = block_reduce_sum<256>(seed_n), r_st = block_reduce_sum<256>(seed_tot);
+        u64 r_wn[2], r_wc[2], r_wsn[2], r_wst[2];
+        for (int d = 0; d < 2; ++d) {
+            r_wn[d] = block_reduce_sum<256>(wd_nodes[d]); r_wc[d] = block_reduce_sum<256>(wd_cov[d]);
+            r_wsn[d] = block_reduce_sum<256>(wd_seed_n[d]); r_wst[d] = block_reduce_sum<256>(wd_seed_tot[d]);
+        }
+        if (threadIdx.x == 0) {
+            atomicAdd(&out->seed_nodes, r_sn); atomicAdd(&out->seed_score_total, r_st);
+            atomicAdd(&out->kmer_length_total, r_nodes * (u64)a.k);
+            if (r_nodes) atomicMax(&out->kmer_length_max, (u64)a.k);
+            for (int d = 0; d < 2; ++d) {
+                atomicAdd(&out->nodes_with_dir[d], r_wn[d]); atomicAdd(&out->coverage_with_dir_total[d], r_wc[d]);
+                atomicAdd(&out->seed_nodes_with_dir[d], r_wsn[d]); atomicAdd(&out->seed_score_with_dir_total[d], r_wst[d]);
+            }
+        }
+    }
     if (threadIdx.x == 0) {
         atomicAdd(&out->nodes, r_nodes); atomicAdd(&out->degree_total, r_deg); atomicAdd(&out->coverage_total, r_cov);
         atomicAdd(&out->unflipped, r_unfl); atomicAdd(&out->flipped, r_fl); atomicAdd(&out->path_nodes, r_path);
@@ -872,6 +915,26 @@ __global__ void __launch_bounds__(256) graph_stats_kernel(EmitArgs a, GraphStats
     __syncthreads();
     for (int i = threadIdx.x; i < 17; i += 256) if (s_deg[i]) atomicAdd(&out->degree_bins[i], (u64)s_deg[i]);
     for (int i = threadIdx.x; i < 257; i += 256) if (s_cov[i]) atomicAdd(&out->coverage_bins[i], (u64)s_cov[i]);
+}
+
+// Unclipped "coverage-bins" (GraphStatistics.java:89: one counter per Math.round(coverage) value), the input of the
+// driver's FittingMixture cut-off (GenomixDriver.java:120-137). Low bins are gathered per CTA in shared memory.
+static constexpr int CH_SMEM_BINS = 4096;
+
+template <int KW>
+__global__ void __launch_bounds__(256) coverage_histogram_kernel(EmitArgs a, u64* __restrict__ bins, u64 n_bins) {
+    constexpr int DW = KW + 1;
+    __shared__ u32 s_bins[CH_SMEM_BINS];
+    for (int i = threadIdx.x; i < CH_SMEM_BINS; i += 256) s_bins[i] = 0;
+    __syncthreads();
+    for (u64 n = (u64)blockIdx.x * 256 + threadIdx.x; n < a.n_nodes; n += (u64)gridDim.x * 256) {
+        const u64 cov = a.dense[n * DW + KW] & COUNT_MASK;
+        if (cov < CH_SMEM_BINS) atomicAdd(&s_bins[cov], 1u);
+        else if (cov < n_bins) atomicAdd(bins + cov, 1ull);
+    }
+    __syncthreads();
+    for (u64 i = threadIdx.x; i < CH_SMEM_BINS && i < n_bins; i += 256)
+        if (s_bins[i]) atomicAdd(bins + i, (u64)s_bins[i]);
 }
 
 // R3: KmerPartitionComputerFactory.partition over emitted records (KmerPartitionComputerFactory.java:28-52):

@@ -32,6 +32,7 @@ struct EngineOps {
     void (*emit_scan)(const EmitArgs& a, cudaStream_t st);
     void (*emit_write)(const EmitArgs& a, cudaStream_t st);
     void (*graph_stats)(const EmitArgs& a, GraphStatsDev* out, cudaStream_t st);
+    void (*coverage_histogram)(const EmitArgs& a, u64* bins, u64 n_bins, cudaStream_t st);
     void (*route_heads)(const HeadRouteArgs& a, cudaStream_t st);
     void (*rebase_heads)(void* heads, u64 first, u64 n, u64 store_base, cudaStream_t st);
     int (*prepare)();  // one-time function attributes (dynamic shared memory opt-in)

@@ -59,6 +59,10 @@ void l_graph_stats(const EmitArgs& a, GraphStatsDev* out, cudaStream_t st) {
     if (a.n_nodes == 0) return;
     graph_stats_kernel<KW><<<grid_for(a.n_nodes, 256, 148 * 8), 256, 0, st>>>(a, out);
 }
+void l_coverage_histogram(const EmitArgs& a, u64* bins, u64 n_bins, cudaStream_t st) {
+    if (a.n_nodes == 0) return;
+    coverage_histogram_kernel<KW><<<grid_for(a.n_nodes, 256, 148 * 4), 256, 0, st>>>(a, bins, n_bins);
+}
 void l_route_heads(const HeadRouteArgs& a, cudaStream_t st) {
     if (a.n == 0) return;
     route_heads_kernel<KW><<<(unsigned)((a.n + 255) / 256), 256, 0, st>>>(a);
@@ -95,6 +99,7 @@ const EngineOps OPS = {KW,
                        l_emit_scan,
                        l_emit_write,
                        l_graph_stats,
+                       l_coverage_histogram,
                        l_route_heads,
                        l_rebase_heads,
                        l_prepare};

@@ -48,23 +48,37 @@ static constexpr int LI_THREADS = 256;
 static constexpr int LI_BYTES_PER_THREAD = 32;
 static constexpr int LI_TILE = LI_THREADS * LI_BYTES_PER_THREAD;  // 8 KB of text per CTA
 
-// newline byte-mask of the 32 bytes [pos, pos+32) of text (bit i set <=> text[pos+i] == '\n'), bytes >= n excluded
+// line-terminator byte-mask of the 32 bytes [pos, pos+32) of text, bytes >= n excluded: bit i set <=> text[pos+i] ends a
+// line, i.e. it is '\n', or a '\r' that is not followed by '\n' (hadoop LineReader.readLine and BufferedReader.readLine
+// both accept \n, \r and \r\n; of a \r\n pair the '\n' is the terminator and the '\r' is dropped by the line parser).
 __device__ __forceinline__ u32 newline_mask32(const uint8_t* __restrict__ text, u64 n, u64 pos) {
-    u32 m = 0;
+    u32 nl = 0, cr = 0;
     if (pos >= n) return 0;
     const uint8_t* p = text + pos;
     if (pos + 32 <= n && (((uintptr_t)p) & 3) == 0) {
         const u32* w = reinterpret_cast<const u32*>(p);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const u32 eq = __vcmpeq4(__ldg(w + i), 0x0a0a0a0au);  // 0xff per matching byte
-            m |= ((eq & 1u) | ((eq >> 7) & 2u) | ((eq >> 14) & 4u) | ((eq >> 21) & 8u)) << (4 * i);
+            const u32 x = __ldg(w + i);
+            const u32 eq = __vcmpeq4(x, 0x0a0a0a0au);  // 0xff per matching byte
+            nl |= ((eq & 1u) | ((eq >> 7) & 2u) | ((eq >> 14) & 4u) | ((eq >> 21) & 8u)) << (4 * i);
+            const u32 ec = __vcmpeq4(x, 0x0d0d0d0du);
+            cr |= ((ec & 1u) | ((ec >> 7) & 2u) | ((ec >> 14) & 4u) | ((ec >> 21) & 8u)) << (4 * i);
         }
     } else {
         const int lim = (int)min((u64)32, n - pos);
-        for (int i = 0; i < lim; ++i) m |= (u32)(__ldg(p + i) == '\n') << i;
+        for (int i = 0; i < lim; ++i) {
+            const uint8_t c = __ldg(p + i);
+            nl |= (u32)(c == '\n') << i;
+            cr |= (u32)(c == '\r') << i;
+        }
     }
-    return m;
+    if (cr) {   // rare: which of the '\r' are followed by '\n'?
+        u32 next_nl = nl >> 1;
+        if ((cr >> 31) && pos + 32 < n && __ldg(p + 32) == '\n') next_nl |= 1u << 31;
+        nl |= cr & ~next_nl;
+    }
+    return nl;
 }
 
 static __global__ void __launch_bounds__(LI_THREADS) count_newlines_kernel(const uint8_t* __restrict__ text, u64 n,
@@ -95,7 +109,7 @@ static __global__ void __launch_bounds__(LI_THREADS) write_newlines_kernel(const
 static __global__ void finish_line_index_kernel(const uint8_t* __restrict__ text, u64 n, const u64* __restrict__ total_nl,
                                          u32* __restrict__ nl_pos, Counters* __restrict__ ctr) {
     u64 lines = *total_nl;
-    if (n > 0 && text[n - 1] != '\n') { nl_pos[lines] = (u32)n; lines += 1; }
+    if (n > 0 && text[n - 1] != '\n' && text[n - 1] != '\r') { nl_pos[lines] = (u32)n; lines += 1; }
     ctr->chunk_lines = lines;
     ctr->chunk_reads = 0;
     ctr->chunk_occ = 0;

@@ -205,6 +205,19 @@ class GraphBuilder:
         self._check(self._lib.gx_graph_statistics(self._ctx, C.byref(g)))
         return g.as_dict()
 
+    def coverage_histogram(self) -> np.ndarray:
+        """GraphStatistics' "coverage-bins": nodes per Math.round(coverage) value, 0 .. coverage_max."""
+        n = self.graph_statistics()["coverage_max"] + 1
+        out = np.zeros(n, dtype=np.uint64)
+        self._check(self._lib.gx_coverage_histogram(self._ctx, C.c_void_p(out.ctypes.data), C.c_uint64(n)))
+        return out
+
+    def coverage_cutoff(self, iterations: int = 10) -> dict:
+        """GenomixDriver.setCutoffCoverageByFittingMixture: {"cutoff": minimum coverage or 0, fitted mixture parameters}."""
+        cut, em, nm, ns = C.c_int64(0), C.c_double(0), C.c_double(0), C.c_double(0)
+        self._check(self._lib.gx_coverage_cutoff(self._ctx, iterations, C.byref(cut), C.byref(em), C.byref(nm), C.byref(ns)))
+        return {"cutoff": int(cut.value), "exp_mean": em.value, "normal_mean": nm.value, "normal_std": ns.value}
+
     def phase_ms(self) -> dict:
         arr = (C.c_float * 8)()
         self._check(self._lib.gx_phase_ms(self._ctx, C.byref(arr)))

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GX_ABI_VERSION 1
+#define GX_ABI_VERSION 2
 
 typedef struct gx_ctx gx_ctx;
 
@@ -163,8 +163,28 @@ typedef struct gx_graph_stats {
     uint64_t self_edges[4];          /* totals/selfEdge-FF,FR,RF,RR */
     uint64_t path_nodes;             /* inDegree == 1 && outDegree == 1 */
     uint64_t tips_forward, tips_reverse, tips_both, tips_one;
+    /* GraphStatistics.java:87-119. Index 0 = DIR.FORWARD, 1 = DIR.REVERSE: "<x>-with-<DIR>" counts nodes with
+     * degree(DIR) != 0. Every node of a graph build holds one k-letter k-mer, so kmerLength[-with-DIR] follows from the
+     * node counts. scaffoldSeedScore = Node.calculateSeedScore (Node.java:859-862) of the nodes whose coverage lies in
+     * COVERAGE_DIST_MEAN +- COVERAGE_DIST_STD = 0 +- 1000 (GraphStatistics.java:75-76,93-96). */
+    uint64_t kmer_length_total, kmer_length_max;
+    uint64_t nodes_with_dir[2], coverage_with_dir_total[2], coverage_with_dir_max[2];
+    uint64_t seed_nodes, seed_score_total, seed_score_max;
+    uint64_t seed_nodes_with_dir[2], seed_score_with_dir_total[2], seed_score_with_dir_max[2];
 } gx_graph_stats;
 int gx_graph_statistics(gx_ctx* ctx, gx_graph_stats* out);   /* after gx_finish */
+
+/* The unclipped "coverage-bins" group of GraphStatistics (one counter per Math.round(coverage) value): bins[c] = nodes of
+ * coverage c for c < n_bins (call gx_graph_statistics first for coverage_max). After gx_finish. */
+int gx_coverage_histogram(gx_ctx* ctx, uint64_t* host_bins, uint64_t n_bins);
+
+/* The driver's coverage cut-off (GenomixDriver.setCutoffCoverageByFittingMixture, GenomixDriver.java:120-137, running
+ * FittingMixture.fittingMixture, genomix-driver/.../mixture/model/FittingMixture.java:92-216, on this rank's coverage bins):
+ * an exponential + normal mixture fitted with `iterations` EM rounds (the driver uses 10); *cutoff = the first coverage at
+ * which the normal component outweighs the exponential one, 0 if there is none (the driver then leaves
+ * REMOVE_BAD_COVERAGE_MIN_COVERAGE unset). GX_ERR_STATE ("No information for coverage!") on an empty graph.
+ * exp_mean / normal_mean / normal_std (may be NULL) receive the fitted parameters (GenomixDriver.cur_*). */
+int gx_coverage_cutoff(gx_ctx* ctx, int32_t iterations, int64_t* cutoff, double* exp_mean, double* normal_mean, double* normal_std);
 
 /* ---- multi-GPU (n_ranks > 1): hash-partitioned exchange ----------------------------------------
  * One process per GPU. Bootstrap: rank 0 calls gx_mg_unique_id, the host side broadcasts the 128

@@ -29,16 +29,13 @@ public class GpuReadsKeyValueParserFactory implements IKeyValueParserFactory<Lon
     private static final int LINE_BUFFER_BYTES = 64 << 20;
 
     private final ConfFactory confFactory;
-    private final int gpusPerNode;
+    private final int nNodes;
     private final int nPartitions;
-    private final byte[] ncclUniqueId; // created once by the job generator (GenomixGb.mgUniqueId()) and serialised with us
 
-    public GpuReadsKeyValueParserFactory(JobConf conf, int gpusPerNode, int nPartitions, byte[] ncclUniqueId)
-            throws HyracksDataException {
+    public GpuReadsKeyValueParserFactory(JobConf conf, int nNodes, int nPartitions) throws HyracksDataException {
         this.confFactory = new ConfFactory(conf);
-        this.gpusPerNode = gpusPerNode;
+        this.nNodes = nNodes;
         this.nPartitions = nPartitions;
-        this.ncclUniqueId = ncclUniqueId;
     }
 
     @Override
@@ -46,9 +43,21 @@ public class GpuReadsKeyValueParserFactory implements IKeyValueParserFactory<Lon
             throws HyracksDataException {
         final int k = Integer.parseInt(confFactory.getConf().get(GenomixJobConf.KMER_LENGTH));
         final int partition = ctx.getTaskAttemptId().getTaskId().getPartition();
-        final long gx = GenomixGb.create(k, partition % gpusPerNode, partition, nPartitions, 0L);
+        // node-major partition layout (JobGen.java:67-69): this node's (partition / nNodes)-th partition -> its own GPU
+        final long gx = GenomixGb.create(k, partition / nNodes, partition, nPartitions, 0L);
         if (nPartitions > 1) {
-            GenomixGb.mgInit(gx, ncclUniqueId);
+            try {
+                // partition 0 creates the NCCL id (it has the GPU and the library), everybody else picks it up
+                byte[] ncclUniqueId = partition == 0 ? NcclIdExchange.publish(confFactory.getConf(), GenomixGb.mgUniqueId())
+                        : NcclIdExchange.await(confFactory.getConf());
+                GenomixGb.mgInit(gx, ncclUniqueId); // collective: returns once every partition has joined
+                if (partition == 0) {
+                    NcclIdExchange.done(confFactory.getConf());
+                }
+            } catch (java.io.IOException e) {
+                GenomixGb.destroy(gx);
+                throw new HyracksDataException(e);
+            }
         }
         final ByteBuffer lines = ByteBuffer.allocateDirect(LINE_BUFFER_BYTES);
         final ByteBuffer frame = ctx.allocateFrame(); // heap, array-backed, like the reference (:68-70)

@@ -26,21 +26,31 @@ import edu.uci.ics.hyracks.hdfs.scheduler.Scheduler;
 public class JobGenBuildBrujinGraphGpu extends JobGenBuildBrujinGraph {
     private static final long serialVersionUID = 1L;
     private final int gpusPerNode;
+    private final int numPartitionPerMachine;
 
     public JobGenBuildBrujinGraphGpu(GenomixJobConf job, Scheduler scheduler, final Map<String, NodeControllerInfo> ncMap,
             int numPartitionPerMachine, int gpusPerNode) throws HyracksDataException {
         super(job, scheduler, ncMap, numPartitionPerMachine);
         this.gpusPerNode = gpusPerNode;
+        this.numPartitionPerMachine = numPartitionPerMachine;
     }
 
     @Override
-    protected JobSpecification assignJob(JobSpecification jobSpec) throws HyracksException {
+    public JobSpecification assignJob(JobSpecification jobSpec) throws HyracksException { // public, like JobGenBuildBrujinGraph.java:79
         try {
             int nPartitions = readSchedule.length;
-            byte[] ncclId = nPartitions > 1 ? GenomixGb.mgUniqueId() : null;
+            // JobGen.java:67-69 lays the partitions out node-major (partition p runs on node p % nNodes and is that node's
+            // (p / nNodes)-th partition): one partition per GPU, never two NCCL ranks on one device
+            int nNodes = ncNodeNames.length / numPartitionPerMachine;
+            if (numPartitionPerMachine > gpusPerNode) {
+                throw new IllegalArgumentException("threadsPerMachine (" + numPartitionPerMachine + ") exceeds the GPUs per machine ("
+                        + gpusPerNode + "): the GPU graph build runs one partition per GPU");
+            }
+            // the client that generates the job needs neither a GPU nor NCCL: partition 0's task creates the NCCL id and
+            // publishes it next to the job's output (NcclIdExchange), the other partitions wait for it
             HDFSReadOperatorDescriptor read = new HDFSReadOperatorDescriptor(jobSpec,
                     ReadsKeyValueParserFactory.readKmerOutputRec, hadoopJobConfFactory.getConf(), getInputSplit(), readSchedule,
-                    new GpuReadsKeyValueParserFactory(hadoopJobConfFactory.getConf(), gpusPerNode, nPartitions, ncclId));
+                    new GpuReadsKeyValueParserFactory(hadoopJobConfFactory.getConf(), nNodes, nPartitions));
             PartitionConstraintHelper.addAbsoluteLocationConstraint(jobSpec, read, ncNodeNames);
 
             HDFSWriteOperatorDescriptor write = new HDFSWriteOperatorDescriptor(jobSpec, hadoopJobConfFactory.getConf(),

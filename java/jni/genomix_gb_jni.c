@@ -2,6 +2,7 @@
  * Exceptions mirror what the reference's pure-Java path throws. */
 #include <jni.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "genomix_gb.h"
 
 #define CTX(h) ((gx_ctx*)(intptr_t)(h))
@@ -12,7 +13,13 @@ static void throw_gx(JNIEnv* env, gx_ctx* c, int st) {
                     : (st == GX_ERR_READ_TOO_SHORT || st == GX_ERR_READID_RANGE || st == GX_ERR_INVALID)
                           ? "java/lang/IllegalArgumentException"
                           : "edu/uci/ics/hyracks/api/exceptions/HyracksDataException";
-    (*env)->ThrowNew(env, (*env)->FindClass(env, cls), gx_last_error(c));
+    jclass ex = (*env)->FindClass(env, cls);
+    if (!ex) {   /* class not on the path (FindClass left a NoClassDefFoundError pending): fall back to a JDK class */
+        (*env)->ExceptionClear(env);
+        ex = (*env)->FindClass(env, "java/lang/RuntimeException");
+        if (!ex) return;
+    }
+    (*env)->ThrowNew(env, ex, gx_last_error(c));
 }
 
 JNIEXPORT jlong JNICALL Java_edu_uci_ics_genomix_hyracks_gpu_GenomixGb_create(JNIEnv* env, jclass k, jint kmer, jint device,
@@ -53,11 +60,15 @@ JNIEXPORT jint JNICALL Java_edu_uci_ics_genomix_hyracks_gpu_GenomixGb_nextFrame(
                                                                                 jbyteArray frame, jint frameSize) {
     jlong cur;
     (*env)->GetLongArrayRegion(env, cursor, 0, 1, &cur);
-    jbyte* f = (*env)->GetPrimitiveArrayCritical(env, frame, NULL);
+    /* gx_next_frame blocks on device-to-host copies: it fills a native scratch frame, which is then copied into the Java
+     * array -- no JNI critical region is held across the blocking call (that would stall the garbage collector) */
+    uint8_t* f = (uint8_t*)malloc((size_t)frameSize);
+    if (!f) { throw_gx(env, NULL, GX_ERR_NOMEM); return -1; }
     int32_t n = 0;
     uint64_t c64 = (uint64_t)cur;
-    int st = gx_next_frame(CTX(h), &c64, (uint8_t*)f, frameSize, &n);
-    (*env)->ReleasePrimitiveArrayCritical(env, frame, f, 0);
+    int st = gx_next_frame(CTX(h), &c64, f, frameSize, &n);
+    if (!st) (*env)->SetByteArrayRegion(env, frame, 0, frameSize, (const jbyte*)f);
+    free(f);
     if (st) { throw_gx(env, CTX(h), st); return -1; }
     cur = (jlong)c64;
     (*env)->SetLongArrayRegion(env, cursor, 0, 1, &cur);

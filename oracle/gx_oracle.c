@@ -540,14 +540,14 @@ static void* worker_main(void* arg) {
     size_t pos = w->begin;
     uint64_t line_no = w->first_line;
     while (pos < w->end) {
-        const uint8_t* nl = (const uint8_t*)memchr(job->text + pos, '\n', w->end - pos);
-        size_t e = nl ? (size_t)(nl - job->text) : w->end;
-        size_t le = e;
-        if (le > pos && job->text[le - 1] == '\r') le--; /* hadoop LineReader: CRLF */
+        /* hadoop LineReader.readLine: a record ends at \n, \r or \r\n */
+        size_t e = pos;
+        while (e < w->end && job->text[e] != '\n' && job->text[e] != '\r') e++;
         w->lines++;
-        if (parse_line(w, line_no, job->text + pos, le - pos)) break;
+        if (parse_line(w, line_no, job->text + pos, e - pos)) break;
         line_no++;
         pos = e + 1;
+        if (e < w->end && job->text[e] == '\r' && pos < job->n && job->text[pos] == '\n') pos++;
     }
     if (!w->err) {
         qsort(w->tuples.t, w->tuples.n, sizeof(Tuple), tuple_cmp);
@@ -596,8 +596,9 @@ int gxo_build(const uint8_t* text, size_t n, int k, int n_threads, uint8_t** out
         Worker* w = &job.w[t];
         w->job = &job; w->tid = t; w->begin = prev; w->end = end; w->first_line = line_base;
         w->outbox = (TupleVec*)calloc((size_t)n_threads, sizeof(TupleVec));
-        for (size_t i = prev; i < end; i++) line_base += text[i] == '\n';
-        if (end > prev && text[end - 1] != '\n') line_base++;
+        for (size_t i = prev; i < end; i++)
+            line_base += text[i] == '\n' || (text[i] == '\r' && !(i + 1 < n && text[i + 1] == '\n'));
+        if (end > prev && text[end - 1] != '\n' && text[end - 1] != '\r') line_base++;
         prev = end;
     }
     pthread_t* th = (pthread_t*)calloc((size_t)n_threads, sizeof(pthread_t));

@@ -389,12 +389,12 @@ def parse_line(k: int, line: bytes, emit) -> None:
 
 
 def split_lines(text: bytes) -> list:
-    """hadoop TextInputFormat / LineReader: records end at \\n (a preceding \\r is dropped); a final
-    unterminated line is still a record."""
-    lines = text.split(b"\n")
+    """hadoop TextInputFormat / LineReader.readLine (hadoop-core 0.20.2, org.apache.hadoop.util.LineReader): a record ends
+    at \\n, \\r or \\r\\n; a final unterminated line is still a record."""
+    lines = re.split(rb"\r\n|\n|\r", text)
     if lines and lines[-1] == b"":
         lines.pop()
-    return [ln[:-1] if ln.endswith(b"\r") else ln for ln in lines]
+    return lines
 
 
 def build_graph(k: int, text: bytes) -> dict:
@@ -506,3 +506,110 @@ def compare_unordered(expected_lines, actual_lines, unordered=(1, 2, 3, 4)) -> N
                 assert tx == ty, f"unordered field {i} differs:\n< {e}\n> {a}"
             else:
                 assert x == y, f"field {i} differs:\n< {e}\n> {a}"
+
+
+# ---------------------------------------------------------------------------------------------
+# Post-build statistics: GraphStatistics.map and the driver's FittingMixture cut-off, restated literally.
+
+def graph_statistics(k: int, nodes: dict) -> dict:
+    """GraphStatistics.map (genomix-hadoop/.../utils/GraphStatistics.java:78-131) over {key bytes: Node}: the Hadoop counter
+    groups as nested dicts -- "totals", "maximum" and one "<name>-bins" group per updateStats name (:133-141)."""
+    totals, maximum, bins = {}, {}, {}
+
+    def incr(name, by=1):
+        totals[name] = totals.get(name, 0) + by
+
+    def update(name, value):
+        bins.setdefault(name, {})
+        bins[name][value] = bins[name].get(value, 0) + 1
+        incr(name, value)
+        maximum[name] = max(maximum.get(name, 0), value)
+
+    mean, std = 0.0, 1000.0   # COVERAGE_DIST_MEAN / _STD (:75-76)
+    for key, node in nodes.items():
+        sizes = [len(e) if e else 0 for e in node.edges]
+        out_deg, in_deg = sizes[0] + sizes[1], sizes[2] + sizes[3]   # DIR.FORWARD = {FF, FR}, DIR.REVERSE = {RF, RR} (Node.java:820-836)
+        n_un, n_fl = len(node.unflipped or []), len(node.flipped or [])
+        incr("nodes")
+        update("degree", in_deg + out_deg)
+        update("kmerLength", k)                      # the internal kmer of a graph-build node is empty: the key's length (:88-89)
+        cov_round = int(java_round(node.coverage))
+        update("coverage", cov_round)
+        update("unflippedReadIds", n_un)
+        update("flippedReadIds", n_fl)
+        seed = k * (n_un + n_fl)                     # Node.calculateSeedScore (Node.java:859-862)
+        in_window = mean - std <= node.coverage <= mean + std
+        if in_window:
+            update("scaffoldSeedScore", seed)
+        for et, name in enumerate(("FF", "FR", "RF", "RR")):
+            for e in (node.edges[et] or []):
+                if e.write() == key:
+                    incr("selfEdge-" + name)
+        if in_deg == 1 and out_deg == 1:
+            incr("pathNode")
+        for d, deg in (("FORWARD", out_deg), ("REVERSE", in_deg)):
+            if deg == 0:
+                incr("tips-" + d)
+            else:
+                update("kmerLength-with-" + d, k)
+                update("coverage-with-" + d, cov_round)
+                if in_window:
+                    update("scaffoldSeedScore-with-" + d, seed)
+        if in_deg == 0 and out_deg == 0:
+            incr("tips-BOTH")
+        if (in_deg == 0) != (out_deg == 0):
+            incr("tips-ONE")
+    return {"totals": totals, "maximum": maximum, "bins": bins}
+
+
+def java_round(x: float) -> int:
+    """Math.round(float): floor(x + 0.5)"""
+    import math
+    return int(math.floor(x + 0.5))
+
+
+def fitting_mixture(data, max_coverage: float, iterations: int):
+    """FittingMixture.fittingMixture (genomix-driver/.../mixture/model/FittingMixture.java:92-216), one entry of `data` per
+    node exactly like GraphStatistics.getCoverageStats builds it; commons-math3 densities. Returns
+    (cutoff, exp_mean, normal_mean, normal_std)."""
+    import math
+
+    def exp_density(mean, x):
+        return 0.0 if x < 0 else math.exp(-x / mean) / mean
+
+    def normal_density(mean, sd, x):
+        z = (x - mean) / sd
+        return math.exp(-0.5 * z * z) / (sd * math.sqrt(2 * math.pi))
+
+    n = len(data)
+    e_mean, n_mean, n_sd, p_exp, p_norm = 5.0, 20.0, 5.0, 0.5, 0.5
+    m_exp, m_norm = [0.0] * n, [0.0] * n
+
+    def expectation():
+        nonlocal p_exp, p_norm
+        for i in range(n):
+            a = exp_density(e_mean, data[i]) * p_exp
+            if a == 0:
+                a = 0.000000001
+            b = normal_density(n_mean, n_sd, data[i]) * p_norm
+            if b == 0:
+                b = 0.000000001
+            m_exp[i], m_norm[i] = a / (a + b), b / (a + b)
+        es, ns = math.fsum(m_exp), math.fsum(m_norm)
+        p_exp, p_norm = es / (es + ns), ns / (es + ns)
+        return es, ns
+
+    es, ns = expectation()
+    for _ in range(iterations):
+        e_mean = math.fsum(m_exp[i] * data[i] for i in range(n)) / es
+        n_mean = math.fsum(m_norm[i] * data[i] for i in range(n)) / ns
+        n_sd = math.sqrt(math.fsum(m_norm[i] * (data[i] - n_mean) ** 2 for i in range(n)) / ns)
+        if n_sd == 0:
+            n_sd = float(np.float32(0.000000001))
+        es, ns = expectation()
+    cov = 1.0
+    while cov < max_coverage:
+        if p_exp * exp_density(e_mean, cov) < p_norm * normal_density(n_mean, n_sd, cov):
+            return int(cov), e_mean, n_mean, n_sd
+        cov += 1
+    return 0, e_mean, n_mean, n_sd

@@ -112,3 +112,19 @@ def test_differential_fuzz_python_vs_c_oracle():
             assert expected and ei.value.status == expected[0], (err, ei.value.status)
             n_err += 1
     assert n_ok > 40 and n_err > 10
+
+
+def test_line_terminators_python_vs_c_oracle():
+    """\\n, \\r and \\r\\n all end a record (hadoop LineReader.readLine); both oracles agree, for every thread count."""
+    import numpy as np
+    from genomix_b200 import types as T
+    rng = np.random.default_rng(11)
+    reads = [bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(6, 30))).tolist()) for _ in range(120)]
+    eols = [b"\n", b"\r", b"\r\n"]
+    text = b"".join(b"%d\t%s" % (4 * i + 2, r) + eols[int(rng.integers(0, 3))] for i, r in enumerate(reads))
+    want = {key: T.Node.read(val, 0)[0].canonical_bytes() for key, val in O.graph_records(4, O.build_graph(4, text)).items()}
+    assert len(O.split_lines(text)) == 120
+    for threads in (1, 3, 8):
+        got, st = CO.build_graph_records(4, text, threads)
+        assert st["lines"] == 120
+        assert T.canonical_records(got) == want

@@ -174,6 +174,36 @@ def test_edge_inputs():
     assert got == oracle_canonical(5, text)
 
 
+def test_lone_carriage_return_ends_a_line():
+    """hadoop LineReader.readLine and BufferedReader.readLine (GenomixDriver.java:723-735) accept \\n, \\r and \\r\\n."""
+    gx = _gx()
+    rng = np.random.default_rng(5)
+    reads = [bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(9, 40))).tolist()) for _ in range(200)]
+    eols = [b"\n", b"\r", b"\r\n"]
+    text = b"".join(b"%d\t%s" % (4 * i + 2, r) + eols[int(rng.integers(0, 3))] for i, r in enumerate(reads))
+    for t in (text, text.rstrip(b"\r\n"), b"\r".join(b"%d\t%s" % (4 * i + 2, r) for i, r in enumerate(reads)) + b"\r",
+              b"\r".join(b"%d\t%s" % (4 * i + 2, r) for i, r in enumerate(reads))):   # also: \r-only files
+        want = oracle_canonical(5, t)
+        assert len(want) > 100
+        assert gpu_canonical(5, t)[0] == want
+        assert oracle_canonical_c(5, t) == want
+    # a '\r' on a 32-byte boundary of the line index whose '\n' starts the next 32 bytes is one terminator, not two
+    line = b"2\t" + b"ACGT" * 7 + b"A"          # 31 bytes + '\r' = 32
+    t = line + b"\r\n" + b"6\tGGATTACAGG\r\n"
+    assert len(line) == 31
+    with gx.GraphBuilder(5) as gb:
+        gb.push_lines(t)
+        gb.finish()
+        assert gb.stats()["lines"] == 2
+        assert gx.types.canonical_records(gb.records()) == oracle_canonical(5, t)
+    # fastq with \r-terminated lines
+    fq = b"".join(b"@r%d\r%s\r+\r%s\r" % (i, r, b"I" * len(r)) for i, r in enumerate(reads))
+    with gx.GraphBuilder(5) as gb:
+        gb.push_fastq(fq)
+        gb.finish()
+        assert gx.types.canonical_records(gb.records()) == oracle_canonical(5, O.fastq_to_readids(fq))
+
+
 def test_long_read_windows():
     """FrameSizePressureTest shape: one read far longer than a warp window"""
     rng = np.random.default_rng(9)
@@ -264,42 +294,57 @@ def test_cfg1_full_size():
 
 
 def test_graph_statistics_match_reference_definitions():
-    """gx_graph_statistics against GraphStatistics.java:78-131 evaluated on the decoded records"""
+    """gx_graph_statistics / gx_coverage_histogram against the oracle's restatement of GraphStatistics.map
+    (GraphStatistics.java:78-131) evaluated on the decoded records, and gx_coverage_cutoff against its restatement of the
+    driver's FittingMixture cut-off (GenomixDriver.java:120-137)"""
     gx = _gx()
     rng = np.random.default_rng(31)
     text = random_reads_text(rng, 500, 40, 70, paired=True, genome_len=1500) + b"9000\t" + b"AC" * 30 + b"\n9004\t" + b"A" * 40 + b"\n"
+    text += b"".join(b"%d\t%s\n" % (4 * (5000 + i) + 2, b"GATTACAGGATCCATTTGCA" * 3) for i in range(1500))   # coverage > 1000 and > 256
     for k in (4, 21, 33):
         with gx.GraphBuilder(k) as gb:
             gb.push_lines(text)
             gb.finish()
             got = gb.graph_statistics()
-            recs = list(gx.types.iter_records(gb.records()))
-        want = {"nodes": 0, "degree_total": 0, "degree_max": 0, "degree_bins": [0] * 17, "coverage_total": 0, "coverage_max": 0,
-                "coverage_bins": [0] * 257, "unflipped_read_ids": 0, "flipped_read_ids": 0, "self_edges": [0] * 4, "path_nodes": 0,
-                "tips_forward": 0, "tips_reverse": 0, "tips_both": 0, "tips_one": 0}
-        for key, val in recs:
-            node, _ = gx.types.Node.read(val, 0)
-            sizes = [len(e) if e else 0 for e in node.edges]
-            out_deg, in_deg = sizes[0] + sizes[1], sizes[2] + sizes[3]   # DIR.FORWARD = {FF, FR}, DIR.REVERSE = {RF, RR}
-            want["nodes"] += 1
-            want["degree_total"] += in_deg + out_deg
-            want["degree_max"] = max(want["degree_max"], in_deg + out_deg)
-            want["degree_bins"][in_deg + out_deg] += 1
-            cov = int(round(node.coverage))
-            want["coverage_total"] += cov
-            want["coverage_max"] = max(want["coverage_max"], cov)
-            want["coverage_bins"][min(cov, 256)] += 1
-            want["unflipped_read_ids"] += len(node.unflipped or [])
-            want["flipped_read_ids"] += len(node.flipped or [])
-            for et in range(4):
-                want["self_edges"][et] += sum(1 for e in (node.edges[et] or []) if e.write() == key)
-            want["path_nodes"] += in_deg == 1 and out_deg == 1
-            want["tips_forward"] += out_deg == 0
-            want["tips_reverse"] += in_deg == 0
-            want["tips_both"] += in_deg == 0 and out_deg == 0
-            want["tips_one"] += (in_deg == 0) != (out_deg == 0)
+            hist = gb.coverage_histogram()
+            cut = gb.coverage_cutoff(10)
+            nodes = {key: gx.types.Node.read(val, 0)[0] for key, val in gx.types.iter_records(gb.records())}
+        ref = O.graph_statistics(k, nodes)
+        T, M, B = ref["totals"], ref["maximum"], ref["bins"]
+        want = {
+            "nodes": T["nodes"], "degree_total": T["degree"], "degree_max": M["degree"],
+            "degree_bins": [B["degree"].get(i, 0) for i in range(17)],
+            "coverage_total": T["coverage"], "coverage_max": M["coverage"],
+            "coverage_bins": [B["coverage"].get(i, 0) for i in range(256)] + [sum(v for c, v in B["coverage"].items() if c >= 256)],
+            "unflipped_read_ids": T["unflippedReadIds"], "flipped_read_ids": T["flippedReadIds"],
+            "self_edges": [T.get("selfEdge-" + n, 0) for n in ("FF", "FR", "RF", "RR")],
+            "path_nodes": T.get("pathNode", 0), "tips_forward": T.get("tips-FORWARD", 0), "tips_reverse": T.get("tips-REVERSE", 0),
+            "tips_both": T.get("tips-BOTH", 0), "tips_one": T.get("tips-ONE", 0),
+            "kmer_length_total": T["kmerLength"], "kmer_length_max": M["kmerLength"],
+            "nodes_with_dir": [sum(B.get("kmerLength-with-" + d, {}).values()) for d in ("FORWARD", "REVERSE")],
+            "coverage_with_dir_total": [T.get("coverage-with-" + d, 0) for d in ("FORWARD", "REVERSE")],
+            "coverage_with_dir_max": [M.get("coverage-with-" + d, 0) for d in ("FORWARD", "REVERSE")],
+            "seed_nodes": sum(B.get("scaffoldSeedScore", {}).values()),
+            "seed_score_total": T.get("scaffoldSeedScore", 0), "seed_score_max": M.get("scaffoldSeedScore", 0),
+            "seed_nodes_with_dir": [sum(B.get("scaffoldSeedScore-with-" + d, {}).values()) for d in ("FORWARD", "REVERSE")],
+            "seed_score_with_dir_total": [T.get("scaffoldSeedScore-with-" + d, 0) for d in ("FORWARD", "REVERSE")],
+            "seed_score_with_dir_max": [M.get("scaffoldSeedScore-with-" + d, 0) for d in ("FORWARD", "REVERSE")],
+        }
         assert got == want, k
-        assert want["self_edges"] != [0, 0, 0, 0]
+        assert want["self_edges"] != [0, 0, 0, 0] and want["coverage_max"] > 1000
+        assert want["seed_nodes"] < want["nodes"]                  # the coverage window excludes the deep nodes
+        # coverage-bins, unclipped
+        assert [int(x) for x in hist] == [B["coverage"].get(i, 0) for i in range(M["coverage"] + 1)]
+        # the cut-off: the driver expands the bins into one entry per node (GraphStatistics.getCoverageStats)
+        data = [float(c) for c, n in sorted(B["coverage"].items()) for _ in range(n)]
+        w_cut, w_em, w_nm, w_ns = O.fitting_mixture(data, float(M["coverage"]), 10)
+        assert cut["cutoff"] == w_cut
+        assert abs(cut["exp_mean"] - w_em) <= 1e-9 * abs(w_em) and abs(cut["normal_mean"] - w_nm) <= 1e-9 * abs(w_nm)
+        assert abs(cut["normal_std"] - w_ns) <= 1e-9 * abs(w_ns)
+    with gx.GraphBuilder(5) as gb:   # empty graph: "No information for coverage!"
+        gb.finish()
+        with pytest.raises(gx.GenomixError):
+            gb.coverage_cutoff()
 
 
 @pytest.mark.parametrize("k", [31, 55, 91, 128])

@@ -122,3 +122,18 @@ def test_java_float_to_string():
     assert O.java_float_to_string(52.0) == "52.0"
     assert O.java_float_to_string(1.0e7) == "1.0E7"
     assert O.java_float_to_string(12345678.0) == "1.2345678E7"
+
+
+def test_fitting_mixture_cutoff_separates_error_kmers():
+    """FittingMixture.fittingMixture restated (FittingMixture.java:92-216): an exponential error peak at low coverage and a
+    normal genomic peak; the cut-off is the first coverage at which the normal component outweighs the exponential one."""
+    rng = np.random.default_rng(0)
+    data = [float(x) for x in np.concatenate([np.round(rng.exponential(3, 5000)) + 1, np.round(rng.normal(50, 10, 5000))]).clip(1)]
+    cut, e_mean, n_mean, n_sd = O.fitting_mixture(data, max(data), 10)
+    assert 15 <= cut <= 35 and 3 < e_mean < 6 and 48 < n_mean < 53 and 8 < n_sd < 11
+    # no second component: every coverage is explained by the exponential -> 0 (the driver then sets no cut-off)
+    assert O.fitting_mixture([1.0] * 50, 1.0, 10)[0] == 0
+    # permutation invariance (the Hadoop counters arrive in string order of their names)
+    shuffled = list(data)
+    rng.shuffle(shuffled)
+    assert O.fitting_mixture(shuffled, max(data), 10)[0] == cut
