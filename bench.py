@@ -395,14 +395,27 @@ def main():
     upsert_ms = phase.get("insert", 0.0) + phase.get("exchange_insert", 0.0)
     build_ms = upsert_ms + phase.get("split", 0.0)
     upsert_bytes = rank_occ * (kb + 16) + n_up * kb     # per occurrence: its key + the 16-byte slot update; per new key: the key
-    traffic, traffic_src = None, None
+    # DRAM traffic of the kernels, from the committed ncu --set full capture of this workload (profiles/traffic.json, written
+    # by scripts/ncu_to_profiles.py: one entry per launch of one step; cold-cache and serialised, so bytes, not times)
+    traffic, traffic_src, kernel_traffic = None, None, {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if world == 1 and os.path.exists(tpath):
         try:
-            tj = json.load(open(tpath))
-            traffic, traffic_src = tj.get(f"{args.workload}_upsert_regions_bytes_per_step"), tj.get(f"{args.workload}_upsert_regions_source")
+            tj = json.load(open(tpath)).get(f"{args.workload}_kernels")
+            if tj:
+                traffic_src = tj["source"]
+                for kname, launches_ in tj["launches"].items():
+                    kernel_traffic[kname] = {"dram_bytes_per_step": sum(x["dram_bytes"] for x in launches_), "launches": len(launches_),
+                                             "ncu_ms": sum(x["ms"] for x in launches_), "files": [x["file"] for x in launches_]}
+                up = [v for k_, v in kernel_traffic.items() if k_.startswith("upsert_regions_kernel")]
+                traffic = sum(v["dram_bytes_per_step"] for v in up) if up else None
         except Exception:
-            traffic = None
+            traffic, kernel_traffic = None, {}
+    # algorithmic bytes of the other two phases (BASELINE.md §3 split by phase): split reads each base twice (count + place)
+    # and writes one (Kb + 2)-byte record per occurrence; finish reads every slot once and writes the records
+    nb_ = (w.k + 3) // 4
+    split_bytes = n_occ * (2 * w.read_len / (w.read_len - w.k + 1) + kb + 2)
+    finish_bytes = stats["table_capacity"] * {8: 16, 16: 32, 24: 32, 32: 48}[kb] + stats["record_bytes"] if "record_bytes" in stats else None
     roof = {
         "bound": "hbm", "kernel": "upsert_regions_kernel<KW> (region-sorted k-mer records -> hash-table upserts)",
         "achieved": upsert_bytes / (upsert_ms * 1e-3) / 1e9 if upsert_ms > 0 else None,
@@ -415,6 +428,14 @@ def main():
         "build_phase": {"kernels": "split_count + split_place + upsert_regions (what round 1's fused extract_kernel did)",
                         "algorithmic_bytes_per_step": build_bytes, "ms_per_step": build_ms, "bytes_per_occurrence": b_occ,
                         "frac": build_bytes / (build_ms * 1e-3) / 1e9 / peak if build_ms > 0 else None},
+        "phases": {
+            "split": {"kernels": "split_count + split_place", "algorithmic_bytes_per_step": split_bytes, "ms_per_step": phase.get("split", 0.0),
+                      "frac": split_bytes / (phase["split"] * 1e-3) / 1e9 / peak if phase.get("split") else None},
+            "finish": {"kernels": "heads_* + emit_scan + emit_write", "algorithmic_bytes_per_step": finish_bytes,
+                       "ms_per_step": phase.get("finish", 0.0),
+                       "frac": finish_bytes / (phase["finish"] * 1e-3) / 1e9 / peak if (finish_bytes and phase.get("finish")) else None},
+        },
+        "kernel_traffic": kernel_traffic or None,
         "job_bytes_per_step": job_bytes,
         "job_frac": job_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
     }

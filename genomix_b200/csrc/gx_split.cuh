@@ -21,7 +21,16 @@
 
 namespace gx {
 
-static constexpr int SP_THREADS = 512;
+#ifndef GX_SP_THREADS
+#define GX_SP_THREADS 512
+#endif
+#ifndef GX_SP_MIN1
+#define GX_SP_MIN1 2
+#endif
+#ifndef GX_SP_MIN2
+#define GX_SP_MIN2 2
+#endif
+static constexpr int SP_THREADS = GX_SP_THREADS;
 static constexpr int SP_WARPS = SP_THREADS / 32;
 static constexpr int SP_NPL = 4;                // consecutive positions per lane and round
 static constexpr int SP_MAX_BUCKETS = 1024;     // owners x regions handled by one multisplit
@@ -44,7 +53,9 @@ struct SplitArgs {
     unsigned short* owner_meta[SP_MAX_RANKS];  // with direct NVLink delivery, this rank's share of the owner's inbox
 };
 
-template <int KW> struct SplitBlocks { static constexpr int MIN = (KW == 1) ? 2 : 1; };
+// CTAs per SM (profiles/r02_tune_split.txt): k <= 64 runs two 512-thread CTAs (KW = 2 at 64 registers with a few spilled
+// words is 18 % faster than one CTA at 102 registers: the rounds are barrier-separated, a second CTA fills the gaps)
+template <int KW> struct SplitBlocks { static constexpr int MIN = (KW == 1) ? GX_SP_MIN1 : (KW == 2) ? GX_SP_MIN2 : 1; };
 
 template <int KW>
 struct SplitSmem {
@@ -275,11 +286,14 @@ __global__ void __launch_bounds__(SP_THREADS, SplitBlocks<KW>::MIN) split_place_
             }
         }
         __syncthreads();
-        // exclusive scan over the buckets (two per thread) and ONE global reservation per non-empty bucket
-        static_assert(SP_MAX_BUCKETS == 2 * SP_THREADS, "two buckets per thread");
-        const u32 b0 = 2u * tid, b1 = b0 + 1u;
-        const u32 c0 = S.cnt[b0], c1 = S.cnt[b1];
-        u32 incl = c0 + c1;
+        // exclusive scan over the buckets (SP_BPT consecutive ones per thread) and ONE global reservation per non-empty bucket
+        constexpr int SP_BPT = SP_MAX_BUCKETS / SP_THREADS;
+        static_assert(SP_BPT * SP_THREADS == SP_MAX_BUCKETS, "whole buckets per thread");
+        u32 cb[SP_BPT];
+        u32 incl = 0;
+#pragma unroll
+        for (int q = 0; q < SP_BPT; ++q) { cb[q] = S.cnt[SP_BPT * tid + q]; incl += cb[q]; }
+        const u32 mine = incl;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const u32 t = __shfl_up_sync(0xffffffffu, incl, d);
@@ -287,7 +301,7 @@ __global__ void __launch_bounds__(SP_THREADS, SplitBlocks<KW>::MIN) split_place_
         }
         if (lane == 31) S.warp_sums[warp] = incl;
         __syncthreads();
-        u32 wsum = lane < SP_WARPS ? S.warp_sums[lane] : 0u;   // every warp scans the 16 warp sums itself
+        u32 wsum = lane < SP_WARPS ? S.warp_sums[lane] : 0u;   // every warp scans the warp sums itself
 #pragma unroll
         for (int d = 1; d < SP_WARPS; d <<= 1) {
             const u32 t = __shfl_up_sync(0xffffffffu, wsum, d);
@@ -295,16 +309,16 @@ __global__ void __launch_bounds__(SP_THREADS, SplitBlocks<KW>::MIN) split_place_
         }
         const u32 total = __shfl_sync(0xffffffffu, wsum, SP_WARPS - 1);
         const u32 wex = warp ? __shfl_sync(0xffffffffu, wsum, warp - 1) : 0u;
-        const u32 ex = wex + incl - (c0 + c1);
-        if (c0) {   // b < n_buckets because only such buckets were counted
-            S.start[b0] = ex;
-            S.gbase[b0] = atomicAdd(a.cursor + (size_t)b0 * CURSOR_PAD, (u64)c0);
-            S.cnt[b0] = 0;
-        }
-        if (c1) {
-            S.start[b1] = ex + c0;
-            S.gbase[b1] = atomicAdd(a.cursor + (size_t)b1 * CURSOR_PAD, (u64)c1);
-            S.cnt[b1] = 0;
+        u32 ex = wex + incl - mine;
+#pragma unroll
+        for (int q = 0; q < SP_BPT; ++q) {
+            if (cb[q]) {   // b < n_buckets because only such buckets were counted
+                const u32 b = SP_BPT * tid + q;
+                S.start[b] = ex;
+                S.gbase[b] = atomicAdd(a.cursor + (size_t)b * CURSOR_PAD, (u64)cb[q]);
+                S.cnt[b] = 0;
+                ex += cb[q];
+            }
         }
         __syncthreads();
 #pragma unroll
