@@ -12,7 +12,7 @@ GX_ABI_VERSION = 2
 # every symbol include/genomix_gb.h declares (tests check that the .so exports each one)
 EXPORTS = [
     "gx_abi_version", "gx_create", "gx_destroy", "gx_reset", "gx_last_error", "gx_get_stats",
-    "gx_push_lines", "gx_push_lines_device", "gx_push_fastq", "gx_finish",
+    "gx_push_lines", "gx_push_lines_device", "gx_push_fastq", "gx_push_records", "gx_finish",
     "gx_num_nodes", "gx_record_bytes", "gx_next_records", "gx_records_device", "gx_next_frame",
     "gx_partition_records", "gx_write_sequence_file", "gx_graph_statistics", "gx_coverage_histogram", "gx_coverage_cutoff",
     "gx_mg_unique_id", "gx_mg_init", "gx_mg_exchange",
@@ -93,6 +93,7 @@ def load() -> C.CDLL:
         "gx_push_lines": (C.c_int, [vp, u8p, sz]),
         "gx_push_lines_device": (C.c_int, [vp, u8p, sz]),
         "gx_push_fastq": (C.c_int, [vp, u8p, sz, u8p, sz, u64]),
+        "gx_push_records": (C.c_int, [vp, u8p, sz]),
         "gx_finish": (C.c_int, [vp]),
         "gx_num_nodes": (C.c_int64, [vp]),
         "gx_record_bytes": (C.c_int64, [vp]),
@@ -102,6 +103,8 @@ def load() -> C.CDLL:
         "gx_partition_records": (C.c_int, [vp, i32, vp]),
         "gx_write_sequence_file": (C.c_int, [vp, C.c_char_p, u8p, i32, i32, C.POINTER(u64)]),
         "gx_graph_statistics": (C.c_int, [vp, C.POINTER(GxGraphStats)]),
+        "gx_coverage_histogram": (C.c_int, [vp, vp, u64]),
+        "gx_coverage_cutoff": (C.c_int, [vp, i32, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "gx_mg_unique_id": (C.c_int, [u8p]),
         "gx_mg_init": (C.c_int, [vp, u8p]),
         "gx_mg_exchange": (C.c_int, [vp]),

@@ -111,6 +111,8 @@ struct gx_ctx {
     Arena arena;               // single GPU: the current chunk's records (reused chunk after chunk)
     u32 fixed_regions = 0;     // != 0: table regions per rank for the whole job (multi-GPU, or cfg.reserved[3])
     DevBuf tile_prefix, deferred[2], region_new;
+    DevBuf mrec, moff, mbase, mkeys, mmeta, mcounts;   // gx_push_records staging
+    u64 merged_records = 0;
     u64 upserted_records = 0;
 
     u64 global_lines = 0;
@@ -276,6 +278,10 @@ int line_error_to_status(gx_ctx* c, u64 packed) {
             c->sticky = fail(c, GX_ERR_READID_RANGE,
                              "IllegalArgumentException: byte specified for readId will lose some of its bits when saved! "
                              "(input line %llu)", (unsigned long long)line);
+            break;
+        case LE_RECORD:
+            c->sticky = fail(c, GX_ERR_FORMAT, "malformed or unsupported Node record (record %llu of the pushed stream): gx_push_records takes "
+                             "graph-build records of this kmer length", (unsigned long long)line);
             break;
         default:
             c->sticky = fail(c, GX_ERR_INVALID, "unknown line error %u (input line %llu)", code, (unsigned long long)line);
@@ -773,6 +779,7 @@ int gx_reset(gx_ctx* c) {
     c->hash_mul = (u64)c->cfg.n_ranks;
     c->new_key_rate = 1.0;
     c->upserted_records = 0;
+    c->merged_records = 0;
     c->spill_cur = 0;
     GX_TRY(set_spill_target(c));
     GX_TRY(mg_reset(c));
@@ -799,7 +806,8 @@ void gx_destroy(gx_ctx* c) {
     DevBuf* bufs[] = {&c->heads, &c->store, &c->text, &c->text2, &c->nl_pos, &c->nl_pos2, &c->desc, &c->tile_sums, &c->ht_key, &c->ht_count, &c->ht_start,
                       &c->hgroup, &c->hentry, &c->hperm, &c->hoff, &c->bkey, &c->big_list, &c->tile_state, &c->records, &c->rec_offsets,
                       &c->parts, &c->dense, &c->dense_h, &c->big_tiles, &c->ring[0], &c->ring[1], &c->slice_idx,
-                      &c->tile_prefix, &c->deferred[0], &c->deferred[1], &c->region_new, &c->gstats};
+                      &c->tile_prefix, &c->deferred[0], &c->deferred[1], &c->region_new, &c->gstats,
+                      &c->mrec, &c->moff, &c->mbase, &c->mkeys, &c->mmeta, &c->mcounts};
     for (auto* b : bufs) release(*b);
     release_arena(c->arena);
     for (int i = 0; i < 2; ++i) { release(c->spill_keys[i]); release(c->spill_meta[i]); release(c->spill_counts[i]); }
@@ -932,6 +940,76 @@ int gx_push_fastq(gx_ctx* c, const uint8_t* host_r1, size_t n1, const uint8_t* h
     GX_TRY(push_fastq_chunk_device(c, (const uint8_t*)c->text.p, total, n1, base2, host_r2 ? n2 : 0, first_record));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     drain_timers(c);
+    return GX_OK;
+}
+
+// R2, merge half: AggregateKmerAggregateFactory.aggregate (:128-144) of serialised Nodes into the job's table.
+int gx_push_records(gx_ctx* c, const uint8_t* host_records, size_t n_bytes) {
+    GX_TRY(require_live(c));
+    if (c->finished) return fail(c, GX_ERR_STATE, "gx_push_records after gx_finish (call gx_reset first)");
+    if (!host_records && n_bytes) return fail(c, GX_ERR_INVALID, "null records");
+    if (c->cfg.n_ranks > 1) return fail(c, GX_ERR_INVALID, "gx_push_records on a multi-rank ctx: fold the records in on one rank per key range");
+    if (n_bytes == 0) return GX_OK;
+    cudaSetDevice(c->cfg.device);
+    // record boundaries: a chain of length fields (host walk: 4 bytes per record)
+    std::vector<u64> off;
+    off.reserve(n_bytes / 48 + 2);
+    for (size_t pos = 0; pos < n_bytes;) {
+        if (pos + 8 > n_bytes) return c->sticky = fail(c, GX_ERR_FORMAT, "truncated record header at byte %zu of the pushed stream", pos);
+        const uint8_t* p = host_records + pos;
+        const u64 len = 8ull + (((u64)p[0] << 24) | ((u64)p[1] << 16) | ((u64)p[2] << 8) | (u64)p[3]);
+        if (pos + len > n_bytes) return c->sticky = fail(c, GX_ERR_FORMAT, "record at byte %zu runs past the end of the pushed stream", pos);
+        off.push_back(pos);
+        pos += len;
+    }
+    const u64 n = off.size();
+    off.push_back(n_bytes);
+    GX_TRY(ensure(c, c->mrec, n_bytes));
+    GX_TRY(ensure(c, c->moff, (n + 1) * sizeof(u64)));
+    GX_TRY(ensure(c, c->mbase, 2 * n * sizeof(u64)));
+    GX_TRY(ensure(c, c->mkeys, n * c->kw * sizeof(u64)));
+    GX_TRY(ensure(c, c->mmeta, n * sizeof(unsigned short)));
+    GX_TRY(ensure(c, c->mcounts, n * sizeof(u32)));
+    CUDA_TRY(c, cudaMemcpyAsync(c->mrec.p, host_records, n_bytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->moff.p, off.data(), (n + 1) * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+    MergeArgs a{};
+    a.rec = (const uint8_t*)c->mrec.p; a.rec_off = (const u64*)c->moff.p; a.n_rec = n; a.k = c->k;
+    a.head_base = (u64*)c->mbase.p; a.store_base = (u64*)c->mbase.p + n;
+    a.ctr = c->d_ctr;
+    a.keys = (u64*)c->mkeys.p; a.meta = (unsigned short*)c->mmeta.p; a.counts = (u32*)c->mcounts.p;
+    a.order_base = (1ull << 62) + c->merged_records;   // behind every parsed line
+    GX_TRY(sync_counters(c));
+    const u64 heads0 = c->h_ctr->head_cursor, store0 = c->h_ctr->store_cursor;
+    {
+        ScopedPhase ph(c, PH_PARSE);
+        c->ops->merge_scan(a, c->stream);
+        GX_TRY(check_launch(c, "merge_scan"));
+    }
+    GX_TRY(sync_counters(c));   // also keeps `off` alive until the copy is done
+    if (c->h_ctr->error != ~0ull) return line_error_to_status(c, c->h_ctr->error);
+    GX_TRY(ensure(c, c->heads, (size_t)c->h_ctr->head_cursor * c->ops->head_bytes, (size_t)heads0 * c->ops->head_bytes, true));
+    GX_TRY(ensure(c, c->store, (size_t)c->h_ctr->store_cursor, (size_t)store0));
+    a.heads = c->heads.p; a.store = (uint8_t*)c->store.p;
+    {
+        ScopedPhase ph(c, PH_PARSE);
+        c->ops->merge_apply(a, c->stream);
+        GX_TRY(check_launch(c, "merge_apply"));
+    }
+    // room for the worst case (every record a new key), then the plain upsert of (key, mask, count) records
+    const u64 distinct0 = c->table_live ? c->h_ctr->distinct : 0;
+    const u64 want = std::max<u64>(c->min_capacity, (u64)((double)(distinct0 + n) / TARGET_LOAD) + 1);
+    c->hash_mul = (u64)c->cfg.n_ranks;
+    if (!c->table_live) GX_TRY(ensure_table(c, want));
+    else if ((double)(distinct0 + n) > MAX_LOAD * (double)c->capacity) GX_TRY(grow_table_to(c, want));
+    {
+        ScopedPhase ph(c, PH_INSERT);
+        c->ops->insert_records(a.keys, a.meta, a.counts, n, c->table, c->capacity, c->hash_mul, c->d_ctr, c->stream);
+        GX_TRY(check_launch(c, "insert_records"));
+    }
+    GX_TRY(sync_counters(c));
+    if (c->h_ctr->error != ~0ull) return line_error_to_status(c, c->h_ctr->error);
+    GX_TRY(handle_spills(c));
+    c->merged_records += n;
     return GX_OK;
 }
 

@@ -5,8 +5,10 @@
 //                  K2 upsert_regions: region-by-region, L2-resident hash-table upserts
 //   gx_build.cuh   extraction helpers, insert_records (spills), init_table, rehash
 //   gx_emit.cuh    K3 read-head grouping, sizing, Node serialisation, graph statistics, Java partition hash
+//   gx_merge.cuh   serialised Node records back into (key, mask, count) + read heads (gx_push_records)
 #pragma once
 #include "gx_emit.cuh"
+#include "gx_merge.cuh"
 #include "gx_split.cuh"
 
 namespace gx {
@@ -33,6 +35,8 @@ struct EngineOps {
     void (*emit_write)(const EmitArgs& a, cudaStream_t st);
     void (*graph_stats)(const EmitArgs& a, GraphStatsDev* out, cudaStream_t st);
     void (*coverage_histogram)(const EmitArgs& a, u64* bins, u64 n_bins, cudaStream_t st);
+    void (*merge_scan)(const MergeArgs& a, cudaStream_t st);
+    void (*merge_apply)(const MergeArgs& a, cudaStream_t st);
     void (*route_heads)(const HeadRouteArgs& a, cudaStream_t st);
     void (*rebase_heads)(void* heads, u64 first, u64 n, u64 store_base, cudaStream_t st);
     int (*prepare)();  // one-time function attributes (dynamic shared memory opt-in)

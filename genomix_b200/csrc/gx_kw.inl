@@ -63,6 +63,12 @@ void l_coverage_histogram(const EmitArgs& a, u64* bins, u64 n_bins, cudaStream_t
     if (a.n_nodes == 0) return;
     coverage_histogram_kernel<KW><<<grid_for(a.n_nodes, 256, 148 * 4), 256, 0, st>>>(a, bins, n_bins);
 }
+void l_merge_scan(const MergeArgs& a, cudaStream_t st) {
+    if (a.n_rec) merge_scan_kernel<KW><<<(unsigned)((a.n_rec + 255) / 256), 256, 0, st>>>(a);
+}
+void l_merge_apply(const MergeArgs& a, cudaStream_t st) {
+    if (a.n_rec) merge_apply_kernel<KW><<<(unsigned)((a.n_rec + 255) / 256), 256, 0, st>>>(a);
+}
 void l_route_heads(const HeadRouteArgs& a, cudaStream_t st) {
     if (a.n == 0) return;
     route_heads_kernel<KW><<<(unsigned)((a.n + 255) / 256), 256, 0, st>>>(a);
@@ -100,6 +106,8 @@ const EngineOps OPS = {KW,
                        l_emit_write,
                        l_graph_stats,
                        l_coverage_histogram,
+                       l_merge_scan,
+                       l_merge_apply,
                        l_route_heads,
                        l_rebase_heads,
                        l_prepare};

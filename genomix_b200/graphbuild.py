@@ -102,6 +102,13 @@ class GraphBuilder:
         self._check(self._lib.gx_push_fastq(self._ctx, p1, n1, p2, n2, first_record))
         del k1, k2
 
+    def push_records(self, records) -> None:
+        """Fold a stream of serialised `VKmer | Node` records (the framing records() returns) into the job: the merge
+        half of the reference's aggregator (AggregateKmerAggregateFactory.java:128-144) on the GPU."""
+        ptr, n, keep = _host_ptr(records)
+        self._check(self._lib.gx_push_records(self._ctx, ptr, n))
+        del keep
+
     def finish(self) -> None:
         self._check(self._lib.gx_finish(self._ctx))
 

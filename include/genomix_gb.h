@@ -112,6 +112,16 @@ int gx_push_lines_device(gx_ctx* ctx, const uint8_t* dev_text, size_t n_bytes);
 int gx_push_fastq(gx_ctx* ctx, const uint8_t* host_r1, size_t n1, const uint8_t* host_r2, size_t n2,
                   uint64_t first_record);
 
+/* ---- R2, merge half: serialised Nodes back into the job -------------------------------------------
+ * AggregateKmerAggregateFactory.aggregate (genomix-hyracks/.../graph/dataflow/AggregateKmerAggregateFactory.java:128-144)
+ * merges the accumulated Node of a key with another serialised Node of the same key: per edge type
+ * VKmerList.unionUpdate, ReadHeadSet.unionUpdate (TreeSet.addAll), coverage added. gx_push_records does that for a
+ * whole stream of records (the framing of gx_next_records: recordLength | keyLength | VKmer | Node) against
+ * everything the job holds so far -- earlier pushes of lines, fastq or records. Graph-build Nodes of this kmer length
+ * only (every edge a one-letter shift of the key, no internal kmer, read-head sets stored by value); anything else is
+ * GX_ERR_FORMAT. Single-rank jobs. */
+int gx_push_records(gx_ctx* ctx, const uint8_t* host_records, size_t n_bytes);
+
 /* ---- R2 + shuffle + emit ------------------------------------------------------------------------
  * Aggregate everything pushed so far and serialise this rank's nodes into the record stream.
  * With n_ranks > 1 the multi-GPU exchange must already have been driven (gx_mg_* below). */

@@ -13,6 +13,18 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden", "reference")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "timeout: per-test time limit (pytest-timeout)")
+
+
+def pytest_collection_modifyitems(config, items):
+    """A hung kernel must fail one test, not eat the whole GPU visit: every GPU test gets a time limit (pytest-timeout, if
+    installed; the full-size and multi-rank tests get more)."""
+    if not config.pluginmanager.hasplugin("timeout"):
+        return
+    for item in items:
+        if "gpu" in item.keywords and not any(m.name == "timeout" for m in item.iter_markers()):
+            big = "fullsize" in item.nodeid or "multirank" in item.nodeid
+            item.add_marker(pytest.mark.timeout(900 if big else 240))
 
 
 def golden_cases():

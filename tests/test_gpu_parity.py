@@ -457,3 +457,50 @@ def test_streamed_records_equal_resident_records(k, paired, monkeypatch):
         # the frames carry the same tuples in the same order as the record stream
         recs = list(gx.types.iter_records(whole))
         assert sum(int.from_bytes(f[-4:], "big") for f in frames) == len(recs)
+
+
+@pytest.mark.parametrize("k,paired", [(5, False), (31, True), (55, False), (91, True)])
+def test_push_records_merges_like_the_aggregator(k, paired):
+    """gx_push_records = the merge half of AggregateKmerAggregateFactory (:128-144) on serialised Nodes: graphs built
+    separately from two halves of the input, folded into one job, equal the graph of the whole input -- edge lists united,
+    read-head sets united (the same (readId, mate) on both sides stays once), coverages added."""
+    gx = _gx()
+    rng = np.random.default_rng(4000 + k)
+    t1 = random_reads_text(rng, 700, k + 3, k + 60, paired=paired, genome_len=3000)
+    # second half: other reads of the same genome-free random source plus some lines of the first half again
+    t2 = random_reads_text(rng, 500, k + 3, k + 60, paired=paired, genome_len=3000) + b"\n".join(t1.split(b"\n")[:50]) + b"\n"
+    want = oracle_canonical_c(k, t1 + t2)
+    a, b = gx.build_graph(k, t1), gx.build_graph(k, t2)
+    # records + records into an empty job
+    with gx.GraphBuilder(k) as gb:
+        gb.push_records(a)
+        gb.push_records(b)
+        gb.finish()
+        assert gx.types.canonical_records(gb.records()) == want
+        assert gb.stats()["kmer_occurrences"] == sum(int(gx.types.Node.read(v, 0)[0].coverage) for v in want.values())
+    # lines, then records on top (and in the other order), in small pieces
+    for first_lines in (True, False):
+        with gx.GraphBuilder(k, min_capacity=8192) as gb:
+            if first_lines:
+                gb.push_lines(t1)
+            pieces, pos, offs = [], 0, [0]
+            for key, val in gx.types.iter_records(b):
+                offs.append(offs[-1] + 8 + len(key) + len(val))
+            for cut in offs[::97] + [offs[-1]]:
+                if cut > pos:
+                    gb.push_records(b[pos:cut])
+                    pos = cut
+            if not first_lines:
+                gb.push_lines(t1)
+            gb.finish()
+            assert gx.types.canonical_records(gb.records()) == want, first_lines
+    # what is not a graph-build record of this k is refused, not folded in wrongly
+    with gx.GraphBuilder(k) as gb:
+        with pytest.raises(gx.GenomixError) as ei:
+            gb.push_records(a[:-3])
+        assert ei.value.status == -4
+    other = gx.build_graph(k + 1, t1)
+    with gx.GraphBuilder(k) as gb:
+        with pytest.raises(gx.GenomixError) as ei:
+            gb.push_records(other)
+        assert ei.value.status == -4
