@@ -36,7 +36,7 @@ const EngineOps* engine_ops(int kw) {
 
 namespace {
 
-constexpr double MAX_LOAD = 0.75;     // load limit of a table region while a chunk is upserted (per-region deferral)
+constexpr double MAX_LOAD = 0.80;     // load limit of a table region while a chunk is upserted (per-region deferral)
 constexpr double HARD_LOAD = 0.90;    // the table as a whole never holds more keys than this fraction of its capacity
 constexpr double TARGET_LOAD = 0.60;  // capacity chosen for this load when the number of keys is known or estimated
 constexpr u64 MIN_CAPACITY = 1ull << 20;
@@ -374,7 +374,9 @@ u32 choose_regions(gx_ctx* c, u64 occ) {
     const u32 max_regions = (u32)(SP_MAX_BUCKETS / std::max(1, c->cfg.n_ranks));
     if (c->fixed_regions) return std::min(c->fixed_regions, max_regions);
     const u64 distinct = c->table_live ? c->h_ctr->distinct : 0;
-    const u64 keys = c->cfg.expected_kmers ? std::max<u64>(c->cfg.expected_kmers, distinct) : distinct + occ;
+    // without a hint: sequencing data repeats itself (coverage), so about half of a chunk's occurrences being new keys is
+    // already the pessimistic case; regions that turn out larger than planned cost a little L2 locality, nothing else
+    const u64 keys = c->cfg.expected_kmers ? std::max<u64>(c->cfg.expected_kmers, distinct) : distinct + occ / 2;
     size_t table_bytes = (size_t)((double)keys / TARGET_LOAD) * c->ops->slot_bytes;
     if (c->table_live) table_bytes = std::max(table_bytes, (size_t)c->capacity * c->ops->slot_bytes);
     return (u32)std::min<size_t>(max_regions, std::max<size_t>(1, (table_bytes + REGION_BYTES - 1) / REGION_BYTES));
@@ -487,6 +489,10 @@ int run_upsert_range(gx_ctx* c, const UpsertSrc* src, u32 n_src, u32 n_regions, 
         GX_TRY(handle_spills(c));
         n_deferred = c->h_ctr->deferred_count;
         if (!n_deferred) return GX_OK;
+        if (getenv("GENOMIX_GB_DEBUG"))
+            fprintf(stderr, "[genomix_gb debug] upsert: %llu items deferred (regions %u-%u of %u, capacity %llu, keys %llu, region room %llu, "
+                    "hard limit %llu): growing\n", (unsigned long long)n_deferred, r0, r1, n_regions, (unsigned long long)c->capacity,
+                    (unsigned long long)c->h_ctr->distinct, (unsigned long long)a.region_room, (unsigned long long)a.hard_limit);
         // a region reached its load limit: double the table and apply what was postponed
         GX_TRY(grow_table_to(c, c->capacity * 2));
         CUDA_TRY(c, cudaMemsetAsync(&c->d_ctr->deferred_count, 0, sizeof(u64), c->stream));
