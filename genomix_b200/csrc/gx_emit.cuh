@@ -373,13 +373,29 @@ __global__ void __launch_bounds__(EM_THREADS) emit_scan_kernel(EmitArgs a) {
         if ((u64)tile >= n_tiles) break;
         const u64 slot_base = (u64)tile * ES_TILE + (u64)lane;
         const u32 lane_lt = (1u << lane) - 1u;
-        // ---- pass 1: the tile's aggregate
+        // ---- pass 1: the tile's aggregate. Only the value words are needed (after the build an occupied slot's value word is
+        // non-zero for every key width): all of the lane's loads are in flight together
         u64 tile_bytes = 0, tile_nodes = 0;
+        {
+            constexpr int SW = SlotTraits<KW>::WORDS;
+            constexpr int HALF = ES_SUB * EM_PER_THREAD / 2;
 #pragma unroll 1
-        for (int sub = 0; sub < ES_SUB; ++sub) {
-            ScanSlots<KW> r;
-            scan_load<KW>(a, slot_base + (u64)sub * 32 * EM_PER_THREAD, nb, r);
-            tile_bytes += r.bytes; tile_nodes += r.nodes;
+            for (int h = 0; h < 2; ++h) {
+                u64 v[HALF];
+#pragma unroll
+                for (int q = 0; q < HALF; ++q) {
+                    const u64 slot = slot_base + 32u * (h * HALF + q);
+                    v[q] = slot < a.capacity ? a.table[slot * SW + KW] : 0ull;
+                }
+#pragma unroll
+                for (int q = 0; q < HALF; ++q) {
+                    if (!v[q]) continue;
+                    u32 sz = plain_record_bytes((u32)(v[q] >> MASK_SHIFT), nb);
+                    if (v[q] & HEADS_FLAG)
+                        sz += heads_record_bytes(a.group[head_group_find(a.ht_key, a.ht_mask, slot_base + 32u * (h * HALF + q))]);
+                    tile_bytes += sz; tile_nodes += 1;
+                }
+            }
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
@@ -704,12 +720,21 @@ __device__ __forceinline__ void write_tile_window(const EmitArgs& a, const Write
         else if (v < (long long)wb && v + (long long)t.rec_bytes > 0)
             write_node<KW, true>(a, win, wwords, (int)v, t.key, t.val, t.rec_bytes, t.heads_active);
     }
-    if (__any_sync(0xffffffffu, t.n_heads != 0)) {
+    // Read heads. The common case -- a node with one or two heads in a single-window tile -- is written by the node's own
+    // lane right away (its group is in registers; the dependent loads of several such lanes overlap). Everything else
+    // (many heads, or a tile of several windows) goes through the lane-per-head path below.
+    const bool own_heads = t.n_heads != 0 && t.n_heads <= 2u && t.span <= (u64)win_bytes;
+    if (own_heads) {
+        const HeadGroup g = a.group[t.grp];
+        const int vh = (int)(t.skew + t.hpos);
+        for (u32 hi = 0; hi < t.n_heads; ++hi) write_head_item<KW>(a, win, wwords, vh, g, hi);
+    }
+    if (__any_sync(0xffffffffu, t.n_heads != 0 && !own_heads)) {
         // the heads of my node that touch the window: [h_lo, h_hi). A head's bytes start at
         // vh + 5 + (5 if it is in the second of two sets) + hoff, monotone in the head's position.
         u32 h_lo = 0, h_hi = 0;
         const long long vh = (long long)t.skew + t.hpos - (long long)wlo;
-        if (t.n_heads) {
+        if (t.n_heads && !own_heads) {
             const HeadGroup g = a.group[t.grp];
             const long long hb = (long long)heads_record_bytes(g);
             if (vh < (long long)wb && vh + hb > 0) {
@@ -767,13 +792,19 @@ __device__ __forceinline__ void write_tile_window(const EmitArgs& a, const Write
 }
 
 template <int KW>
-__global__ void __launch_bounds__(EM_THREADS, KW <= 2 ? 4 : 2) emit_write_kernel(EmitArgs a) {
+__global__ void __launch_bounds__(EM_THREADS, KW == 1 ? 4 : (KW == 2 ? 3 : 2)) emit_write_kernel(EmitArgs a) {
     extern __shared__ __align__(16) uint8_t stage_all[];
     __shared__ WriteSmem S;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t* stage = stage_all + (size_t)warp * a.stage_bytes;
     const u64 n_tiles = (a.n_last - a.n_first + 31) / 32;
-    for (u64 tile = (u64)blockIdx.x * EW_WARPS + warp; tile < n_tiles; tile += (u64)gridDim.x * EW_WARPS) {
+    const u64 stride = (u64)gridDim.x * EW_WARPS;
+    for (u64 tile = (u64)blockIdx.x * EW_WARPS + warp; tile < n_tiles; tile += stride) {
+        if (tile + stride < n_tiles) {   // this warp's next tile: its node list and offsets into L2 while this one is written
+            const u64 nn = a.n_first + (tile + stride) * 32;
+            if (lane < 8) prefetch_l2(reinterpret_cast<const char*>(a.dense + nn * (KW + 1)) + 128 * lane);
+            else if (lane < 11) prefetch_l2(reinterpret_cast<const char*>(a.rec_offsets + nn) + 128 * (lane - 8));
+        }
         WriteTile<KW> t;
         write_tile_load<KW>(a, tile, lane, t);
         if (t.span > (u64)EW_MAX_WINDOWS * a.stage_bytes) {

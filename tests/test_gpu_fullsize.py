@@ -76,6 +76,33 @@ def test_cfg2_full_size_properties_and_fingerprint():
     assert CO.canonical_fingerprint(want).key() == got_key
 
 
+def test_cfg4s_k55_high_coverage_fingerprint():
+    """The single-GPU twin of configs[3] (the config the north-star target is quoted on): k=55 (two key words, 128-bit CAS),
+    100x coverage (every key is hot: ~64 occurrences), 4.28e8 occurrences, 6.7e6 nodes. Properties at full size; bit-exact
+    against the C oracle on as many reads as the host can hold the oracle's tuples for."""
+    import psutil
+    import genomix_b200 as gx
+    w = gx.synth.CONFIGS["cfg4s"]
+    text = gx.synth.readid_text(w)
+    stream, st = gpu_build_numpy(gx, w.k, text)
+    assert st["kmer_occurrences"] == gx.synth.occurrences(w)
+    fp = check_properties(stream, st, w.n_reads)
+    del stream
+    s2, _ = gpu_build_numpy(gx, w.k, text, chunk_bytes=96 << 20, table_regions=5)     # other chunking / region count: same graph
+    assert CO.canonical_fingerprint(s2).key() == fp.key()
+    del s2
+    avail = psutil.virtual_memory().available
+    n_sub = w.n_reads if avail > (160 << 30) else (w.n_reads // 4 if avail > (48 << 30) else w.n_reads // 16)
+    sub = text if n_sub == w.n_reads else gx.synth.readid_text(w, n_reads=n_sub)
+    want, ost = CO.build_graph_records(w.k, sub, os.cpu_count() or 1, as_numpy=True)
+    if n_sub == w.n_reads:
+        got_key = fp.key()
+    else:
+        s3, _ = gpu_build_numpy(gx, w.k, sub)
+        got_key = CO.canonical_fingerprint(s3).key()
+    assert CO.canonical_fingerprint(want).key() == got_key
+
+
 @pytest.mark.parametrize("name", ["cfg3s", "cfg5s"])
 def test_scaled_multi_gpu_configs_properties(name):
     """k=55 paired-end and k=91 high-error twins of configs[2] and configs[4] (single-GPU sized): properties at size,
