@@ -50,13 +50,15 @@ struct DevBuf {
 
 // One chunk's k-mer records, sorted by bucket = (owner rank, table region); see gx_split.cuh.
 struct Arena {
-    DevBuf keys, meta;          // [occ] records: KW key words, 16-bit edge mask
-    DevBuf seg_start;           // u64 [n_buckets + 1] record index of each bucket's first record
-    DevBuf cursor;              // u64 [n_buckets * CURSOR_PAD] placement cursors
-    DevBuf bucket_count;        // u64 [n_buckets]
-    u64 occ = 0;
+    DevBuf keys, meta;          // records: KW key words, 16-bit edge mask; bucket b's records sit at the start of its room
+    DevBuf tab;                 // u64 [n_ranks][2 R + 1]: per owner the R region starts, the end of its block, the R region counts
+    DevBuf owner_dev;           // u64 [n_ranks + 1] start of every owner's block (device copy of owner_off)
+    DevBuf cursor, limit;       // u64 [n_buckets * CURSOR_PAD] placement cursors, [n_buckets] end of each bucket's room
+    DevBuf bucket_count;        // u64 [n_buckets] (sampled) counts
+    u64 occ = 0;                // records
+    u64 cap = 0;                // record capacity of keys / meta
     u32 n_regions = 0;
-    std::vector<u64> owner_off; // host copy of seg_start[o * n_regions], o = 0..n_ranks (multi-GPU only)
+    std::vector<u64> owner_off; // host copy of owner_dev (multi-GPU only)
 };
 
 enum Phase { PH_PARSE = 0, PH_INSERT = 1, PH_EXCHANGE = 2, PH_FINISH = 3, PH_H2D = 4, PH_XCOMM = 5, PH_XINSERT = 6, PH_SPLIT = 7, PH_COUNT = 8 };
@@ -113,6 +115,7 @@ struct gx_ctx {
     DevBuf tile_prefix, deferred[2], region_new;
     DevBuf mrec, moff, mbase, mkeys, mmeta, mcounts;   // gx_push_records staging
     u64 merged_records = 0;
+    u64 split_redos = 0;           // chunks whose estimated bucket room overflowed and were split again with exact counts
     u64 upserted_records = 0;
 
     u64 global_lines = 0;
@@ -199,7 +202,7 @@ void release(DevBuf& b) {
 }
 
 void release_arena(Arena& a) {
-    release(a.keys); release(a.meta); release(a.seg_start); release(a.cursor); release(a.bucket_count);
+    release(a.keys); release(a.meta); release(a.tab); release(a.owner_dev); release(a.cursor); release(a.limit); release(a.bucket_count);
 }
 
 cudaEvent_t get_event(gx_ctx* c) {
@@ -382,44 +385,66 @@ u32 choose_regions(gx_ctx* c, u64 occ) {
     return (u32)std::min<size_t>(max_regions, std::max<size_t>(1, (table_bytes + REGION_BYTES - 1) / REGION_BYTES));
 }
 
-// K1: the chunk's k-mer records into `ar`, sorted by (owner, region). `owner_keys/meta` = nullptr: everything goes to the
-// arena (cursors count from the arena start); else per-owner record areas (cursors count from each owner's block).
-int split_chunk(gx_ctx* c, const uint8_t* d_text, size_t n, u64 n_lines, u64 chunk_occ, u32 n_regions, Arena& ar) {
+// K1: the chunk's k-mer records into `ar`, sorted by (owner, region). The room of every bucket comes from a count pass over
+// every 16th line (exact = false) -- an estimate with slack; if a bucket still overflows, the chunk is split again with the
+// exact counts of a full count pass, which also is what small chunks get. Leaves the stream synchronised.
+int split_chunk_once(gx_ctx* c, const uint8_t* d_text, size_t n, u64 n_lines, u64 chunk_occ, u32 n_regions, Arena& ar, bool exact) {
     const u32 n_ranks = (u32)c->cfg.n_ranks, n_buckets = n_ranks * n_regions;
+    const u32 sample = (exact || n_lines < 16384) ? 1u : 16u;
     ar.occ = chunk_occ;
     ar.n_regions = n_regions;
-    GX_TRY(ensure(c, ar.keys, (size_t)chunk_occ * c->kw * sizeof(u64)));
-    GX_TRY(ensure(c, ar.meta, (size_t)chunk_occ * sizeof(unsigned short)));
-    GX_TRY(ensure(c, ar.seg_start, (size_t)(SP_MAX_BUCKETS + 1) * sizeof(u64)));
+    ar.cap = sample == 1 ? chunk_occ : chunk_occ + chunk_occ / 8 + (u64)4096 * n_buckets;
+    GX_TRY(ensure(c, ar.keys, (size_t)ar.cap * c->kw * sizeof(u64)));
+    GX_TRY(ensure(c, ar.meta, (size_t)ar.cap * sizeof(unsigned short)));
+    GX_TRY(ensure(c, ar.tab, (size_t)(2 * SP_MAX_BUCKETS + SP_MAX_RANKS) * sizeof(u64)));   // n_ranks * (2 R + 1), n_ranks * R <= SP_MAX_BUCKETS
+    GX_TRY(ensure(c, ar.owner_dev, (size_t)(SP_MAX_RANKS + 1) * sizeof(u64)));
     GX_TRY(ensure(c, ar.cursor, (size_t)SP_MAX_BUCKETS * CURSOR_PAD * sizeof(u64)));
+    GX_TRY(ensure(c, ar.limit, (size_t)SP_MAX_BUCKETS * sizeof(u64)));
     GX_TRY(ensure(c, ar.bucket_count, (size_t)SP_MAX_BUCKETS * sizeof(u64)));
-    ScopedPhase ph(c, PH_SPLIT);
-    CUDA_TRY(c, cudaMemsetAsync(ar.bucket_count.p, 0, (size_t)n_buckets * sizeof(u64), c->stream));
-    SplitArgs a{};
-    a.text = d_text; a.n_text = n;
-    a.desc = (const LineDesc*)c->desc.p; a.n_lines = n_lines;
-    a.first_line = ((u64)c->cfg.rank << 48) | (c->global_lines - n_lines);
-    a.k = c->k;
-    a.heads = c->heads.p;
-    a.store = (uint8_t*)c->store.p;
-    a.ctr = c->d_ctr;
-    a.n_ranks = n_ranks; a.n_regions = n_regions;
-    a.bucket_count = (u64*)ar.bucket_count.p;
-    a.cursor = (u64*)ar.cursor.p;
-    for (u32 o = 0; o < n_ranks; ++o) { a.owner_keys[o] = (u64*)ar.keys.p; a.owner_meta[o] = (unsigned short*)ar.meta.p; }
-    c->ops->split_count(a, c->stream);
-    GX_TRY(check_launch(c, "split_count"));
-    split_prefix_kernel<<<1, 1024, 0, c->stream>>>((const u64*)ar.bucket_count.p, n_buckets, n_regions, 0, (u64*)ar.seg_start.p,
-                                                   (u64*)ar.cursor.p);
-    GX_TRY(check_launch(c, "split_prefix"));
-    c->ops->split_place(a, c->stream);
-    GX_TRY(check_launch(c, "split_place"));
+    {
+        ScopedPhase ph(c, PH_SPLIT);
+        CUDA_TRY(c, cudaMemsetAsync(ar.bucket_count.p, 0, (size_t)n_buckets * sizeof(u64), c->stream));
+        SplitArgs a{};
+        a.text = d_text; a.n_text = n;
+        a.desc = (const LineDesc*)c->desc.p; a.n_lines = n_lines;
+        a.first_line = ((u64)c->cfg.rank << 48) | (c->global_lines - n_lines);
+        a.k = c->k;
+        a.heads = c->heads.p;
+        a.store = (uint8_t*)c->store.p;
+        a.ctr = c->d_ctr;
+        a.n_ranks = n_ranks; a.n_regions = n_regions; a.sample = sample;
+        a.bucket_count = (u64*)ar.bucket_count.p;
+        a.cursor = (u64*)ar.cursor.p;
+        a.limit = (const u64*)ar.limit.p;
+        for (u32 o = 0; o < n_ranks; ++o) { a.owner_keys[o] = (u64*)ar.keys.p; a.owner_meta[o] = (unsigned short*)ar.meta.p; }
+        c->ops->split_count(a, c->stream);
+        GX_TRY(check_launch(c, "split_count"));
+        split_prefix_kernel<<<1, 1024, 0, c->stream>>>((const u64*)ar.bucket_count.p, n_buckets, n_regions, sample, ar.cap, (u64*)ar.tab.p,
+                                                       (u64*)ar.owner_dev.p, (u64*)ar.cursor.p, (u64*)ar.limit.p, c->d_ctr);
+        GX_TRY(check_launch(c, "split_prefix"));
+        c->ops->split_place(a, c->stream);
+        GX_TRY(check_launch(c, "split_place"));
+        split_finish_kernel<<<1, 1024, 0, c->stream>>>((const u64*)ar.cursor.p, (const u64*)ar.limit.p, n_buckets, n_regions, (u64*)ar.tab.p);
+        GX_TRY(check_launch(c, "split_finish"));
+    }
     if (getenv("GENOMIX_GB_DEBUG")) {
         CUDA_TRY(c, cudaMemsetAsync(&c->d_ctr->scratch[0], 0, sizeof(u64), c->stream));
-        c->ops->check_arena((const u64*)ar.keys.p, (const u64*)ar.seg_start.p, n_ranks, n_regions, &c->d_ctr->scratch[0], c->stream);
+        c->ops->check_arena((const u64*)ar.keys.p, (const u64*)ar.tab.p, n_ranks, n_regions, &c->d_ctr->scratch[0], c->stream);
         GX_TRY(sync_counters(c));
-        fprintf(stderr, "[genomix_gb debug] split: %llu records, %u regions x %u ranks, %llu records outside their bucket\n",
-                (unsigned long long)chunk_occ, n_regions, n_ranks, (unsigned long long)c->h_ctr->scratch[0]);
+        fprintf(stderr, "[genomix_gb debug] split: %llu records, %u regions x %u ranks, counted from every %u-th line, overflow %llu, "
+                "%llu records outside their bucket\n", (unsigned long long)chunk_occ, n_regions, n_ranks, sample,
+                (unsigned long long)c->h_ctr->split_overflow, (unsigned long long)c->h_ctr->scratch[0]);
+    }
+    return sync_counters(c);
+}
+
+int split_chunk(gx_ctx* c, const uint8_t* d_text, size_t n, u64 n_lines, u64 chunk_occ, u32 n_regions, Arena& ar) {
+    const bool force_exact = getenv("GENOMIX_GB_EXACT_SPLIT") != nullptr;   // tuning / tests
+    GX_TRY(split_chunk_once(c, d_text, n, n_lines, chunk_occ, n_regions, ar, force_exact));
+    if (c->h_ctr->split_overflow) {
+        ++c->split_redos;
+        GX_TRY(split_chunk_once(c, d_text, n, n_lines, chunk_occ, n_regions, ar, true));
+        if (c->h_ctr->split_overflow) return fail(c, GX_ERR_INVALID, "internal error: the exact split overflowed its arena");
     }
     return GX_OK;
 }
@@ -599,7 +624,8 @@ int insert_parsed_chunk(gx_ctx* c, const uint8_t* d_text, size_t n) {
     if (c->cfg.n_ranks > 1) return mg_stage_chunk(c, d_text, n, n_lines, chunk_occ);
     const u32 n_regions = choose_regions(c, chunk_occ);
     GX_TRY(split_chunk(c, d_text, n, n_lines, chunk_occ, n_regions, c->arena));
-    UpsertSrc src{(const u64*)c->arena.keys.p, (const unsigned short*)c->arena.meta.p, (const u64*)c->arena.seg_start.p, 0};
+    UpsertSrc src{(const u64*)c->arena.keys.p, (const unsigned short*)c->arena.meta.p, (const u64*)c->arena.tab.p,
+                  (const u64*)c->arena.tab.p + n_regions + 1, 0};
     return upsert_sources(c, &src, 1, n_regions, chunk_occ);
 }
 

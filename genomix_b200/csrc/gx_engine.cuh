@@ -23,7 +23,7 @@ struct EngineOps {
     void (*split_count)(const SplitArgs& a, cudaStream_t st);
     void (*split_place)(const SplitArgs& a, cudaStream_t st);
     void (*upsert_regions)(const UpsertArgs& a, unsigned grid, cudaStream_t st);
-    void (*check_arena)(const u64* keys, const u64* seg_start, u32 n_ranks, u32 n_regions, u64* bad, cudaStream_t st);
+    void (*check_arena)(const u64* keys, const u64* tab, u32 n_ranks, u32 n_regions, u64* bad, cudaStream_t st);
     void (*insert_records)(const u64* keys, const unsigned short* meta, const u32* counts, u64 n, u64* table,
                            u64 capacity, u64 hash_mul, Counters* ctr, cudaStream_t st);
     void (*rehash)(const u64* old_table, u64 old_capacity, u64* table, u64 capacity, u64 hash_mul, Counters* ctr, cudaStream_t st);

@@ -19,8 +19,8 @@ void l_split_place(const SplitArgs& a, cudaStream_t st) {
 void l_upsert_regions(const UpsertArgs& a, unsigned grid, cudaStream_t st) {
     upsert_regions_kernel<KW><<<grid, UpsertCfg<KW>::THREADS, sizeof(UpsertSmem<KW>), st>>>(a);
 }
-void l_check_arena(const u64* keys, const u64* seg_start, u32 n_ranks, u32 n_regions, u64* bad, cudaStream_t st) {
-    check_arena_kernel<KW><<<148 * 8, 256, 0, st>>>(keys, seg_start, n_ranks, n_regions, bad);
+void l_check_arena(const u64* keys, const u64* tab, u32 n_ranks, u32 n_regions, u64* bad, cudaStream_t st) {
+    check_arena_kernel<KW><<<148 * 8, 256, 0, st>>>(keys, tab, n_ranks, n_regions, bad);
 }
 void l_insert_records(const u64* keys, const unsigned short* meta, const u32* counts, u64 n, u64* table, u64 capacity,
                       u64 hash_mul, Counters* ctr, cudaStream_t st) {

@@ -230,7 +230,7 @@ int gx_mg_init(gx_ctx* c, const uint8_t id_bytes[128]) {
     GX_TRY(ensure(c, m->ptr_table, (size_t)2 * m->n * sizeof(void*)));
     GX_TRY(ensure(c, m->counts, (size_t)2 * m->n * sizeof(u64)));
     GX_TRY(ensure(c, m->round_vec, V * (size_t)(m->n + 1) * sizeof(u64)));
-    GX_TRY(ensure(c, m->zero_seg, (size_t)(m->n_regions + 1) * sizeof(u64), 0, true));
+    GX_TRY(ensure(c, m->zero_seg, (size_t)(2 * m->n_regions + 1) * sizeof(u64), 0, true));
     GX_TRY(ensure(c, m->token, 256, 0, true));
     m->pub_cap.assign((size_t)m->n * MG_KINDS, 0);
     m->peer_ptr.assign((size_t)m->n * MG_KINDS, nullptr);
@@ -262,7 +262,7 @@ int gx_mg_exchange(gx_ctx* c) {
         switch (kind) {
             case 0: return (size_t)c->kw * sizeof(u64);
             case 1: return sizeof(unsigned short);
-            case 2: return (size_t)(R + 1) * sizeof(u64);
+            case 2: return (size_t)(2 * R + 1) * sizeof(u64);   // the owner's table: R starts, block end, R counts
             case 3: return c->ops->head_bytes;
             default: return 1;
         }
@@ -308,8 +308,7 @@ int gx_mg_exchange(gx_ctx* c) {
         // owner offsets of this round's arena
         if (ar) {
             ar->owner_off.assign((size_t)n + 1, 0);
-            CUDA_TRY(c, cudaMemcpy2DAsync(ar->owner_off.data(), sizeof(u64), ar->seg_start.p, (size_t)R * sizeof(u64), sizeof(u64), (size_t)n + 1,
-                                          cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(c, cudaMemcpyAsync(ar->owner_off.data(), ar->owner_dev.p, ((size_t)n + 1) * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
         }
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
         // ---- 2. everybody learns everybody's counts of this round. The collective also is the barrier that keeps a rank
@@ -434,7 +433,7 @@ int gx_mg_exchange(gx_ctx* c) {
             switch (kind) {
                 case 0: return ar ? (const void*)((const u64*)ar->keys.p + ar->owner_off[to] * c->kw) : nullptr;
                 case 1: return ar ? (const void*)((const unsigned short*)ar->meta.p + ar->owner_off[to]) : nullptr;
-                case 2: return ar ? (const void*)((const u64*)ar->seg_start.p + (size_t)to * R) : m->zero_seg.p;
+                case 2: return ar ? (const void*)((const u64*)ar->tab.p + (size_t)to * (2 * R + 1)) : m->zero_seg.p;
                 case 3: return m->send_heads[to].p;
                 default: return m->send_store[to].p;
             }
@@ -469,14 +468,15 @@ int gx_mg_exchange(gx_ctx* c) {
         f.srcs.clear(); f.rebase.clear();
         f.total = 0;
         if (ar && vec[1 + me]) {
-            f.srcs.push_back(UpsertSrc{(const u64*)ar->keys.p, (const unsigned short*)ar->meta.p, (const u64*)ar->seg_start.p + (size_t)me * R, 0});
+            const u64* tab = (const u64*)ar->tab.p + (size_t)me * (2 * R + 1);
+            f.srcs.push_back(UpsertSrc{(const u64*)ar->keys.p, (const unsigned short*)ar->meta.p, tab, tab + R + 1, 0});
             f.total += vec[1 + me];
         }
         for (int s2 = 0; s2 < n; ++s2) {
             if (s2 == me || !count_kind(s2, 0, me)) continue;
             const u64 off = seg_off(s2, 0, me);
-            f.srcs.push_back(UpsertSrc{(const u64*)m->inbox[0].p + off * c->kw, (const unsigned short*)m->inbox[1].p + off,
-                                       (const u64*)((const uint8_t*)m->inbox[2].p + (size_t)seg_off(s2, 2, me) * unit_bytes(2)), 1});
+            const u64* tab = (const u64*)((const uint8_t*)m->inbox[2].p + (size_t)seg_off(s2, 2, me) * unit_bytes(2));
+            f.srcs.push_back(UpsertSrc{(const u64*)m->inbox[0].p + off * c->kw, (const unsigned short*)m->inbox[1].p + off, tab, tab + R + 1, 1});
             f.total += count_kind(s2, 0, me);
         }
         f.recv_heads = recv_heads; f.recv_store = recv_store; f.heads_at = heads_at; f.store_at = store_at;

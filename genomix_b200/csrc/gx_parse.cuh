@@ -34,6 +34,7 @@ struct Counters {
     unsigned short* spill_meta;
     u32* spill_counts;   // occurrence count carried by each spilled record
     u64 deferred_count;  // work items of the region upsert postponed because the table reached its load limit
+    u64 split_overflow;  // a bucket's estimated room in the record arena was too small (the host redoes the chunk with exact counts)
     u64 upsert_ticket;   // next work item of the running region upsert (gx_split.cuh upsert_regions_kernel)
     u64 big_groups;      // read-head groups too large for one thread (gx_emit.cuh heads_group_big_kernel)
     u64 big_tiles;       // write-pass tiles too large for one warp (gx_emit.cuh emit_write_big_kernel)

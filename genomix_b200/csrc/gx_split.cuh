@@ -47,8 +47,10 @@ struct SplitArgs {
     Counters* ctr;
     u32 n_ranks;            // owner = owner_of(h, n_ranks)
     u32 n_regions;          // table regions per owner; bucket = owner * n_regions + region_of(local hash)
-    u64* bucket_count;      // count pass: [n_buckets] records per bucket
-    u64* cursor;            // place pass: [n_buckets * CURSOR_PAD] next record index of each bucket inside its owner's area
+    u32 sample;             // count pass: every sample-th line is counted (1 = exact counts)
+    u64* bucket_count;      // count pass: [n_buckets] records per bucket (of the sampled lines)
+    u64* cursor;            // place pass: [n_buckets * CURSOR_PAD] next record index of each bucket
+    const u64* limit;       // place pass: [n_buckets] end of each bucket's room in the arena
     u64* owner_keys[SP_MAX_RANKS];             // record area of each owner (KW words per record): the local arena or,
     unsigned short* owner_meta[SP_MAX_RANKS];  // with direct NVLink delivery, this rank's share of the owner's inbox
 };
@@ -63,6 +65,7 @@ struct SplitSmem {
     u64 win[SP_WARPS][WIN_WORDS];
     u64 keys[T * KW];
     u64 gbase[SP_MAX_BUCKETS];   // record index (in the owner's area) that stage position start[b] goes to
+    u64 glimit[SP_MAX_BUCKETS];  // end of the bucket's room
     u32 cnt[SP_MAX_BUCKETS];     // records of this round per bucket (zero between rounds)
     u32 start[SP_MAX_BUCKETS];   // first stage position of the bucket's run
     unsigned short meta[T];
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(SP_THREADS, SplitBlocks<KW>::MIN) split_count_
     const uint8_t* text_lo = a.text;
     const uint8_t* text_hi = a.text + a.n_text;
     constexpr u32 CHUNK = 32u * SP_NPL;
-    for (u64 line = (u64)blockIdx.x * SP_WARPS + warp; line < a.n_lines; line += (u64)gridDim.x * SP_WARPS) {
+    for (u64 line = ((u64)blockIdx.x * SP_WARPS + warp) * a.sample; line < a.n_lines; line += (u64)gridDim.x * SP_WARPS * a.sample) {
         const LineDesc& dd = a.desc[line];
         const u32 flags = dd.flags;
         if ((flags & 3u) == 0) continue;
@@ -165,21 +168,43 @@ __global__ void __launch_bounds__(SP_THREADS, SplitBlocks<KW>::MIN) split_count_
         if (hist[b]) atomicAdd(a.bucket_count + b, (u64)hist[b]);
 }
 
-// Exclusive prefix of the bucket counts -> seg_start[n_buckets + 1] (record index of each bucket's first record in the
-// arena, owner-major, so every owner's records are one contiguous block) and the placement cursors. With `relative`
-// the cursors count from the start of the owner's block (direct delivery into per-owner areas), else from the arena.
+// Room for every bucket in the arena, from the (sampled) counts: bucket b gets cap_b = count_b * sample, plus -- when the
+// counts are an estimate (sample > 1) -- a sixteenth and 2048 records of slack (the estimate of a 2.8 M record bucket from
+// every 16th line is good to a few thousand records; a bucket that still overflows makes the host redo the chunk with
+// exact counts). Per owner o the table tab[o] = { start of its R regions, end of its block, R counts (split_finish_kernel) }
+// is what the owner's upsert reads -- locally or, with its block, on another GPU.
 static __global__ void __launch_bounds__(1024) split_prefix_kernel(const u64* __restrict__ bucket_count, u32 n_buckets, u32 n_regions,
-                                                            int relative, u64* __restrict__ seg_start, u64* __restrict__ cursor) {
+                                                            u32 sample, u64 arena_cap, u64* __restrict__ tab, u64* __restrict__ owner_off,
+                                                            u64* __restrict__ cursor, u64* __restrict__ limit, Counters* ctr) {
     __shared__ u64 sh_start[SP_MAX_BUCKETS + 1];
     const u32 b = threadIdx.x;
-    const u64 v = b < n_buckets ? bucket_count[b] : 0ull;
+    u64 v = b < n_buckets ? bucket_count[b] * sample : 0ull;
+    if (b < n_buckets && sample > 1) v += v / 16 + 2048;
     u64 tot;
     const u64 ex = block_scan_excl<1024>(v, &tot);
     if (b < n_buckets) sh_start[b] = ex;
-    if (b == 0) { sh_start[n_buckets] = tot; seg_start[n_buckets] = tot; }
+    if (b == 0) { sh_start[n_buckets] = tot; ctr->split_overflow = tot > arena_cap ? 1ull : 0ull; }
     __syncthreads();
-    if (b < n_buckets) seg_start[b] = sh_start[b];
-    if (b < n_buckets) cursor[(size_t)b * CURSOR_PAD] = relative ? sh_start[b] - sh_start[(b / n_regions) * n_regions] : sh_start[b];
+    if (b < n_buckets) {
+        const u32 o = b / n_regions, r = b % n_regions;
+        u64* t = tab + (size_t)o * (2 * n_regions + 1);
+        t[r] = sh_start[b];
+        if (r + 1 == n_regions) t[n_regions] = sh_start[b + 1];
+        if (r == 0) owner_off[o] = sh_start[b];
+        cursor[(size_t)b * CURSOR_PAD] = sh_start[b];
+        limit[b] = sh_start[b + 1];
+    }
+    if (b == 0) owner_off[n_buckets / n_regions] = tot;
+}
+
+// after the placement: records per bucket
+static __global__ void __launch_bounds__(1024) split_finish_kernel(const u64* __restrict__ cursor, const u64* __restrict__ limit,
+                                                            u32 n_buckets, u32 n_regions, u64* __restrict__ tab) {
+    const u32 b = threadIdx.x;
+    if (b >= n_buckets) return;
+    const u32 o = b / n_regions, r = b % n_regions;
+    u64* t = tab + (size_t)o * (2 * n_regions + 1);
+    t[n_regions + 1 + r] = min(cursor[(size_t)b * CURSOR_PAD], limit[b]) - t[r];
 }
 
 // K1b. Restates ReadsKeyValueParserFactory.SplitReads (:150-196) and setEdgesForCurAndNext (:209-233): for every position p
@@ -316,6 +341,7 @@ __global__ void __launch_bounds__(SP_THREADS, SplitBlocks<KW>::MIN) split_place_
                 const u32 b = SP_BPT * tid + q;
                 S.start[b] = ex;
                 S.gbase[b] = atomicAdd(a.cursor + (size_t)b * CURSOR_PAD, (u64)cb[q]);
+                S.glimit[b] = a.limit[b];
                 S.cnt[b] = 0;
                 ex += cb[q];
             }
@@ -336,6 +362,7 @@ __global__ void __launch_bounds__(SP_THREADS, SplitBlocks<KW>::MIN) split_place_
         for (u32 i = tid; i < total; i += SP_THREADS) {
             const u32 b = S.bkt[i];
             const u64 g = S.gbase[b] + (i - S.start[b]);
+            if (g >= S.glimit[b]) { a.ctr->split_overflow = 1ull; continue; }   // estimated room exceeded: the host redoes the chunk
             const u32 o = a.n_ranks > 1 ? b / a.n_regions : 0u;
             u64* kd = a.owner_keys[o] + g * KW;
             if constexpr (KW == 2) {
@@ -349,18 +376,20 @@ __global__ void __launch_bounds__(SP_THREADS, SplitBlocks<KW>::MIN) split_place_
     }
 }
 
-// Debug aid (GENOMIX_GB_DEBUG=1): number of arena records that do not sit in the bucket their hash names.
+// Debug aid (GENOMIX_GB_DEBUG=1): number of records inside the buckets' ranges that do not belong to the bucket their hash names.
 template <int KW>
-__global__ void __launch_bounds__(256) check_arena_kernel(const u64* __restrict__ keys, const u64* __restrict__ seg_start, u32 n_ranks,
+__global__ void __launch_bounds__(256) check_arena_kernel(const u64* __restrict__ keys, const u64* __restrict__ tab, u32 n_ranks,
                                                           u32 n_regions, u64* __restrict__ bad) {
     const u32 n_buckets = n_ranks * n_regions;
-    const u64 n = seg_start[n_buckets];
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
-        u64 key[KW];
+    for (u32 b = blockIdx.x; b < n_buckets; b += gridDim.x) {
+        const u64* t = tab + (size_t)(b / n_regions) * (2 * n_regions + 1);
+        const u64 lo = t[b % n_regions], n = t[n_regions + 1 + b % n_regions];
+        for (u64 i = threadIdx.x; i < n; i += blockDim.x) {
+            u64 key[KW];
 #pragma unroll
-        for (int j = 0; j < KW; ++j) key[j] = keys[i * KW + j];
-        const u32 b = bucket_of_hash(hash_key<KW>(key), n_ranks, n_regions);
-        if (i < seg_start[b] || i >= seg_start[b + 1]) atomicAdd(bad, 1ull);
+            for (int j = 0; j < KW; ++j) key[j] = keys[(lo + i) * KW + j];
+            if (bucket_of_hash(hash_key<KW>(key), n_ranks, n_regions) != b) atomicAdd(bad, 1ull);
+        }
     }
 }
 
@@ -401,7 +430,8 @@ static constexpr int UP_MAX_SRC = 64;                        // record areas wal
 
 struct UpsertSrc {
     const u64* keys; const unsigned short* meta;   // the owner's record area (block start)
-    const u64* seg;        // [n_regions + 1] record index of each region's first record; region r holds seg[r+1] - seg[r]
+    const u64* seg;        // [n_regions + 1] record index of each region's first record (and the end of the block)
+    const u64* cnt;        // [n_regions] records of each region (its room in the block may be larger)
     u64 rebase;            // 1: indices in seg count from seg[0] (a block cut out of a larger arena), 0: from the area start
 };
 
@@ -439,7 +469,7 @@ static __global__ void __launch_bounds__(1024) upsert_prefix_kernel(UpsertArgs a
         u64 items = 0;
         if (i < n_pairs) {
             const u32 region = a.r0 + i / a.n_src, s = i % a.n_src;
-            items = (a.src[s].seg[region + 1] - a.src[s].seg[region] + UP_ITEM - 1) / UP_ITEM;
+            items = (a.src[s].cnt[region] + UP_ITEM - 1) / UP_ITEM;
         }
         u64 tot;
         const u64 ex = block_scan_excl<1024>(items, &tot);
@@ -477,9 +507,8 @@ __global__ void __launch_bounds__(UpsertCfg<KW>::THREADS, UpsertCfg<KW>::MIN_BLO
         if (p < n_pairs) {
             const UpsertSrc& S = a.src[p % a.n_src];
             const u32 region = a.r0 + p / a.n_src;
-            const u64 lo = S.seg[region];
-            Q.first[p] = lo - (S.rebase ? S.seg[0] : 0ull);
-            Q.count[p] = (u32)(S.seg[region + 1] - lo);
+            Q.first[p] = S.seg[region] - (S.rebase ? S.seg[0] : 0ull);
+            Q.count[p] = (u32)S.cnt[region];
         }
     }
     __syncthreads();
