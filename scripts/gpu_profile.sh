@@ -4,7 +4,7 @@
 TAG=$1; W=${2:-cfg2}
 mkdir -p gpurun_out
 export GX_BENCH_TEXT_CACHE=/tmp/gxtext
-KRE="split_count|split_place|upsert_regions|emit_scan|emit_write_kernel|parse_lines_kernel"
+KRE="split_count|split_place|upsert_regions|emit_scan|emit_write_kernel|parse_lines_kernel|heads_lookup|heads_group_kernel"
 timeout 900 python bench.py --workload $W --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-nohint > gpurun_out/bench_${TAG}_$W.json 2> gpurun_out/bench_${TAG}_$W.err; echo "bench rc=$?"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches_${TAG}_$W.csv \
     python bench.py --workload $W --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-nohint > gpurun_out/ncu_launches_${TAG}_$W.log 2>&1; echo "ncu launches rc=$?"

@@ -28,3 +28,16 @@ for k, paired in ((21, False), (55, True), (91, False)):
         gb.finish()
         assert len(gx.types.canonical_records(gb.records())) == len(want)
     print("ok", k, flush=True)
+
+# one node with 20000 read heads: CTA-wide head sort, multi-window tile written by emit_write_big_kernel
+k = 21
+rng = np.random.default_rng(7)
+head = bytes(rng.choice(list(b"ACGT"), size=k).tolist())
+text = b"".join(b"%d\t%s\t%s\n" % (4 * i + 2, head + bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(3, 9))).tolist()),
+                                   bytes(rng.choice(list(b"ACGT"), size=30).tolist())) for i in range(20000))
+want = oracle_canonical_c(k, text)
+with gx.GraphBuilder(k) as gb:
+    gb.push_lines(text)
+    gb.finish()
+    assert gx.types.canonical_records(gb.records()) == want
+print("ok big node", flush=True)
