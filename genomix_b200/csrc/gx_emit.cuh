@@ -802,8 +802,9 @@ __global__ void __launch_bounds__(EM_THREADS, KW == 1 ? 4 : (KW == 2 ? 3 : 2)) e
     for (u64 tile = (u64)blockIdx.x * EW_WARPS + warp; tile < n_tiles; tile += stride) {
         if (tile + stride < n_tiles) {   // this warp's next tile: its node list and offsets into L2 while this one is written
             const u64 nn = a.n_first + (tile + stride) * 32;
-            if (lane < 8) prefetch_l2(reinterpret_cast<const char*>(a.dense + nn * (KW + 1)) + 128 * lane);
-            else if (lane < 11) prefetch_l2(reinterpret_cast<const char*>(a.rec_offsets + nn) + 128 * (lane - 8));
+            constexpr int DENSE_LINES = (32 * (KW + 1) * 8 + 127) / 128 + 1;   // 32 nodes, not line-aligned
+            if (lane < DENSE_LINES) prefetch_l2(reinterpret_cast<const char*>(a.dense + nn * (KW + 1)) + 128 * lane);
+            else if (lane < DENSE_LINES + 3) prefetch_l2(reinterpret_cast<const char*>(a.rec_offsets + nn) + 128 * (lane - DENSE_LINES));
         }
         WriteTile<KW> t;
         write_tile_load<KW>(a, tile, lane, t);
