@@ -39,7 +39,7 @@ class GxStats(C.Structure):
         ("lines", C.c_uint64), ("reads", C.c_uint64), ("bases", C.c_uint64), ("kmer_occurrences", C.c_uint64),
         ("distinct_kmers", C.c_uint64), ("read_heads", C.c_uint64), ("record_bytes", C.c_uint64),
         ("table_capacity", C.c_uint64), ("table_grows", C.c_uint64), ("exchanged_records", C.c_uint64),
-        ("reserved", C.c_uint64 * 6),
+        ("split_redos", C.c_uint64), ("reserved", C.c_uint64 * 5),
     ]
 
     def as_dict(self):

@@ -812,6 +812,7 @@ int gx_reset(gx_ctx* c) {
     c->new_key_rate = 1.0;
     c->upserted_records = 0;
     c->merged_records = 0;
+    c->split_redos = 0;
     c->spill_cur = 0;
     GX_TRY(set_spill_target(c));
     GX_TRY(mg_reset(c));
@@ -1537,6 +1538,7 @@ int gx_get_stats(gx_ctx* c, gx_stats* out) {
     out->table_capacity = c->capacity;
     out->table_grows = c->grows;
     out->exchanged_records = mg_exchanged(c);
+    out->split_redos = c->split_redos;
     return GX_OK;
 }
 

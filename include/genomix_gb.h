@@ -83,8 +83,9 @@ typedef struct gx_stats {
     uint64_t record_bytes;      /* bytes of the serialised record stream after gx_finish() */
     uint64_t table_capacity;    /* hash-table slots */
     uint64_t table_grows;       /* number of rehashes */
-    uint64_t exchanged_records; /* k-mer records this rank sent to other ranks */
-    uint64_t reserved[6];
+    uint64_t exchanged_records; /* k-mer records (and slack) this rank sent to other ranks */
+    uint64_t split_redos;       /* chunks whose sampled bucket sizes were too small and that were split again with exact counts */
+    uint64_t reserved[5];
 } gx_stats;
 
 /* ---- lifecycle ------------------------------------------------------------------------------ */

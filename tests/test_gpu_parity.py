@@ -505,3 +505,32 @@ def test_push_records_merges_like_the_aggregator(k, paired):
         with pytest.raises(gx.GenomixError) as ei:
             gb.push_records(other)
         assert ei.value.status == -4
+
+
+@pytest.mark.parametrize("k", [21, 55])
+def test_split_falls_back_to_exact_counts_when_the_sample_misleads(k):
+    """The split sizes its buckets from every 16th line. Here exactly those lines are ordinary reads while all the others repeat
+    one low-complexity read, so one bucket receives hundreds of thousands of records the sample never saw: the placement flags
+    the overflow, the chunk is split again with exact counts, the graph is the oracle's."""
+    gx = _gx()
+    rng = np.random.default_rng(k)
+    hot = b"A" * (k + 40)
+    lines = []
+    for i in range(20000):
+        r = bytes(rng.choice(list(b"ACGT"), size=k + 30).tolist()) if i % 16 == 0 else hot
+        lines.append(b"%d\t%s" % (4 * i + 2, r))
+    text = b"\n".join(lines) + b"\n"
+    with gx.GraphBuilder(k) as gb:
+        gb.push_lines(text)
+        gb.finish()
+        st = gb.stats()
+        got = gx.types.canonical_records(gb.records())
+    assert st["split_redos"] == 1
+    assert got == oracle_canonical_c(k, text)
+    # ordinary data of the same size: the estimate holds
+    text2 = random_reads_text(rng, 20000, k + 5, k + 40, genome_len=50000)
+    with gx.GraphBuilder(k) as gb:
+        gb.push_lines(text2)
+        gb.finish()
+        assert gb.stats()["split_redos"] == 0
+        assert gx.types.canonical_records(gb.records()) == oracle_canonical_c(k, text2)
