@@ -715,6 +715,31 @@ int make_copy_stream(gx_ctx* c) {
     return GX_OK;
 }
 
+// End (exclusive) of the last whole line inside text[lo, hi): the position behind the last '\n', or behind a '\r' that is not
+// followed by '\n' (a "\r\n" pair is never cut in two); ~0 if the window holds no line end. One CTA, walking backwards.
+__global__ void __launch_bounds__(1024) last_line_end_kernel(const uint8_t* __restrict__ text, u64 lo, u64 hi, u64 n, u64* __restrict__ out) {
+    __shared__ unsigned long long best;
+    constexpr u64 PER_THREAD = 64, BLOCK = 1024 * PER_THREAD;
+    for (u64 end = hi; end > lo;) {
+        const u64 begin = end - lo > BLOCK ? end - BLOCK : lo;
+        if (threadIdx.x == 0) best = 0;
+        __syncthreads();
+        const u64 t0 = begin + (u64)threadIdx.x * PER_THREAD;
+        u64 mine = 0;
+        for (u64 p = t0; p < min(t0 + PER_THREAD, end); ++p) {
+            const uint8_t ch = text[p];
+            if (ch == '\n' || (ch == '\r' && !(p + 1 < n && text[p + 1] == '\n'))) mine = p + 1;
+        }
+        if (mine) atomicMax(&best, (unsigned long long)mine);
+        __syncthreads();
+        const u64 b = best;
+        __syncthreads();
+        if (b) { if (threadIdx.x == 0) out[0] = b; return; }
+        end = begin;
+    }
+    if (threadIdx.x == 0) out[0] = ~0ull;
+}
+
 int require_live(gx_ctx* c) {
     if (!c) return GX_ERR_INVALID;
     if (c->sticky) return c->sticky;
@@ -879,18 +904,12 @@ int gx_push_lines_device(gx_ctx* c, const uint8_t* dev_text, size_t n_bytes) {
     while (pos < n_bytes) {
         size_t len = std::min(c->chunk_bytes, n_bytes - pos);
         if (pos + len < n_bytes) {
-            // back up to the last newline inside the window (copy the window tail to the host: at most 64 KiB at a time)
-            size_t scan_end = pos + len;
-            bool found = false;
-            std::vector<uint8_t> tail(65536);
-            while (scan_end > pos && !found) {
-                const size_t w = std::min<size_t>(tail.size(), scan_end - pos);
-                CUDA_TRY(c, cudaMemcpyAsync(tail.data(), dev_text + scan_end - w, w, cudaMemcpyDeviceToHost, c->stream));
-                CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-                for (size_t i = w; i-- > 0;)
-                    if (tail[i] == '\n') { len = scan_end - w + i + 1 - pos; found = true; break; }
-                scan_end -= w;
-            }
+            // back up to the end of the last whole line inside the window (found on the device)
+            last_line_end_kernel<<<1, 1024, 0, c->stream>>>(dev_text, pos, pos + len, n_bytes, &c->d_ctr->scratch[0]);
+            GX_TRY(check_launch(c, "last_line_end"));
+            GX_TRY(sync_counters(c));
+            const bool found = c->h_ctr->scratch[0] != ~0ull;
+            if (found) len = (size_t)(c->h_ctr->scratch[0] - pos);
             if (!found) {  // one line longer than the chunk: extend to its end
                 len = std::min(c->chunk_bytes * 4, n_bytes - pos);
                 if (pos + len < n_bytes) return fail(c, GX_ERR_INVALID, "a single input line exceeds %zu bytes", c->chunk_bytes * 4);

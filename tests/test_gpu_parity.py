@@ -534,3 +534,22 @@ def test_split_falls_back_to_exact_counts_when_the_sample_misleads(k):
         gb.finish()
         assert gb.stats()["split_redos"] == 0
         assert gx.types.canonical_records(gb.records()) == oracle_canonical_c(k, text2)
+
+
+def test_push_lines_device_cuts_chunks_at_line_ends():
+    """gx_push_lines_device on text resident in HBM, with an internal chunk size far below the text: the chunk ends are found
+    on the device, behind a '\\n' or a lone '\\r', never inside a "\\r\\n" pair."""
+    import torch
+    gx = _gx()
+    rng = np.random.default_rng(77)
+    reads = [bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(30, 90))).tolist()) for _ in range(3000)]
+    for eols in ([b"\n"], [b"\r\n"], [b"\n", b"\r", b"\r\n"]):
+        text = b"".join(b"%d\t%s" % (4 * i + 2, r) + eols[i % len(eols)] for i, r in enumerate(reads))
+        want = oracle_canonical_c(21, text)
+        dev = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda()
+        for chunk in (4096, 70000):
+            with gx.GraphBuilder(21, chunk_bytes=chunk) as gb:
+                gb.push_lines_device(dev.data_ptr(), dev.numel())
+                gb.finish()
+                assert gb.stats()["lines"] == 3000
+                assert gx.types.canonical_records(gb.records()) == want
