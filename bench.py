@@ -456,10 +456,10 @@ def main():
                 traffic = sum(v["dram_bytes_per_step"] for v in up) if up else None
         except Exception:
             traffic, kernel_traffic = None, {}
-    # algorithmic bytes of the other two phases (BASELINE.md §3 split by phase): split reads each base twice (count + place)
-    # and writes one (Kb + 2)-byte record per occurrence; finish reads every slot once and writes the records
-    nb_ = (w.k + 3) // 4
-    split_bytes = n_occ * (2 * w.read_len / (w.read_len - w.k + 1) + kb + 2)
+    # algorithmic bytes of the other two phases (BASELINE.md §3 split by phase): split reads each base once for the placement and
+    # every 16th line once more for the bucket sizes, and writes one (Kb + 2)-byte record per occurrence; finish reads every
+    # slot once and writes the records
+    split_bytes = n_occ * ((1 + 1 / 16) * w.read_len / (w.read_len - w.k + 1) + kb + 2)
     finish_bytes = stats["table_capacity"] * {8: 16, 16: 32, 24: 32, 32: 48}[kb] + stats["record_bytes"] if "record_bytes" in stats else None
     roof = {
         "bound": "hbm", "kernel": "upsert_regions_kernel<KW> (region-sorted k-mer records -> hash-table upserts)",
