@@ -84,6 +84,7 @@ struct gx_ctx {
 
     u64* table = nullptr;
     u64 capacity = 0;
+    u64* kept_table = nullptr;     // the job table's allocation while the pilot stands in for it (upsert_sources)
     u64* pilot = nullptr;          // pilot table of a job without capacity hint (upsert_sources); kept for the next job
     u64 pilot_capacity = 0;
     bool table_live = false;  // false: allocation kept from before gx_reset, content stale
@@ -557,6 +558,7 @@ int upsert_sources(gx_ctx* c, const UpsertSrc* src, u32 n_src, u32 n_regions, u6
             const u64 pilot_cap = std::max<u64>(65536, (u64)((double)(share + share / 8 + 4096) / MAX_LOAD) + 1);
             u64* const kept = c->table;             // allocation kept across gx_reset (content stale), if any
             const u64 kept_cap = c->capacity;
+            c->kept_table = kept;                   // owned by the ctx while c->table points at the pilot (freed by gx_destroy on a failure)
             if (c->pilot && (c->pilot_capacity < pilot_cap || c->pilot_capacity > 4 * pilot_cap)) {
                 CUDA_TRY(c, cudaStreamSynchronize(c->stream));
                 CUDA_TRY(c, cudaFree(c->pilot));
@@ -578,6 +580,7 @@ int upsert_sources(gx_ctx* c, const UpsertSrc* src, u32 n_src, u32 n_regions, u6
             c->grows = grows0;
             c->pilot = c->table; c->pilot_capacity = c->capacity;
             c->table = kept; c->capacity = kept_cap; c->table_live = false;
+            c->kept_table = nullptr;
             c->hash_mul = n_ranks;
             const u64 expect = (u64)((double)c->h_ctr->distinct * n_regions * 1.03) + 65536;
             const u64 want = std::max<u64>(cap, (u64)((double)expect / TARGET_LOAD) + 1);
@@ -871,6 +874,7 @@ void gx_destroy(gx_ctx* c) {
     for (int i = 0; i < 2; ++i) { release(c->spill_keys[i]); release(c->spill_meta[i]); release(c->spill_counts[i]); }
     if (c->table) cudaFree(c->table);
     if (c->pilot) cudaFree(c->pilot);
+    if (c->kept_table && c->kept_table != c->table) cudaFree(c->kept_table);
     if (c->d_ctr) cudaFree(c->d_ctr);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
