@@ -140,6 +140,7 @@ struct gx_ctx {
     std::vector<PendingTimer> timers;
     std::vector<cudaEvent_t> event_pool;
     u64 launches = 0;
+    u64 launches_at_sync = ~0ull;
 };
 
 namespace {
@@ -250,8 +251,12 @@ int sync_counters(gx_ctx* c) {
     CUDA_TRY(c, cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     drain_timers(c);
+    c->launches_at_sync = c->launches;
     return GX_OK;
 }
+
+// the host copy of the counters is current if no kernel was launched since it was taken
+int sync_counters_if_stale(gx_ctx* c) { return c->launches == c->launches_at_sync ? GX_OK : sync_counters(c); }
 
 int check_launch(gx_ctx* c, const char* what) {
     ++c->launches;
@@ -435,6 +440,10 @@ int split_chunk_once(gx_ctx* c, const uint8_t* d_text, size_t n, u64 n_lines, u6
         fprintf(stderr, "[genomix_gb debug] split: %llu records, %u regions x %u ranks, counted from every %u-th line, overflow %llu, "
                 "%llu records outside their bucket\n", (unsigned long long)chunk_occ, n_regions, n_ranks, sample,
                 (unsigned long long)c->h_ctr->split_overflow, (unsigned long long)c->h_ctr->scratch[0]);
+    }
+    if (n_ranks > 1) {   // the exchange needs every owner's block boundaries on the host: they travel with this sync
+        ar.owner_off.assign((size_t)n_ranks + 1, 0);
+        CUDA_TRY(c, cudaMemcpyAsync(ar.owner_off.data(), ar.owner_dev.p, ((size_t)n_ranks + 1) * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
     }
     return sync_counters(c);
 }

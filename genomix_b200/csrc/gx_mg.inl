@@ -89,6 +89,7 @@ struct MgState {
         std::vector<Rebase> rebase;
     } inflight;
     std::vector<PendingTimer> comm_timers;
+    std::vector<void*> ptr_host;   // host copy of ptr_table
 };
 
 constexpr int MG_KINDS = 5;
@@ -255,7 +256,7 @@ int gx_mg_exchange(gx_ctx* c) {
     const int n = m->n, me = m->rank;
     const u32 R = m->n_regions;
     const size_t V = (size_t)3 * n + 1;
-    GX_TRY(sync_counters(c));
+    GX_TRY(sync_counters_if_stale(c));   // normally current: the split of the last chunk ended with a counter sync
     GX_TRY(handle_spills(c));
     ScopedPhase ph(c, PH_EXCHANGE);
     auto unit_bytes = [&](int kind) -> size_t {
@@ -286,11 +287,11 @@ int gx_mg_exchange(gx_ctx* c) {
                 // both mates of a pair reference the same two packed sequences and may go to the same owner: 2x
                 GX_TRY(ensure(c, m->send_store[d], (size_t)std::max<u64>(2 * new_store, 1)));
             }
-            std::vector<void*> h((size_t)2 * n);
+            std::vector<void*>& h = m->ptr_host;   // lives in the state: the asynchronous copy below may read it after this scope
+            h.assign((size_t)2 * n, nullptr);
             for (int d = 0; d < n; ++d) { h[d] = m->send_heads[d].p; h[(size_t)n + d] = m->send_store[d].p; }
             CUDA_TRY(c, cudaMemcpyAsync(m->ptr_table.p, h.data(), h.size() * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
             CUDA_TRY(c, cudaMemsetAsync(m->counts.p, 0, (size_t)2 * n * sizeof(u64), c->stream));
-            CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // h is a stack vector
             if (new_heads) {
                 HeadRouteArgs ha{};
                 ha.heads = c->heads.p; ha.first = m->routed_heads_upto; ha.n = new_heads;
@@ -305,12 +306,8 @@ int gx_mg_exchange(gx_ctx* c) {
             }
             CUDA_TRY(c, cudaMemcpyAsync(head_counts.data(), m->counts.p, head_counts.size() * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
         }
-        // owner offsets of this round's arena
-        if (ar) {
-            ar->owner_off.assign((size_t)n + 1, 0);
-            CUDA_TRY(c, cudaMemcpyAsync(ar->owner_off.data(), ar->owner_dev.p, ((size_t)n + 1) * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
-        }
-        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        // (the owner offsets of this round's arena came to the host with the split's sync)
+        if (round == 0) CUDA_TRY(c, cudaStreamSynchronize(c->stream));   // head_counts
         // ---- 2. everybody learns everybody's counts of this round. The collective also is the barrier that keeps a rank
         //         from pushing into an inbox its owner is still reading: every rank enters it after its own mg_complete.
         std::vector<u64> vec(V, 0), all(V * (size_t)n);
@@ -485,8 +482,8 @@ int gx_mg_exchange(gx_ctx* c) {
             const u64 gh = count_kind(p, 3, me);
             if (gh) f.rebase.push_back(MgState::Rebase{heads_at + seg_off(p, 3, me), gh, store_at + seg_off(p, 4, me)});
         }
-        // the host copy of the cursors has to show the reservation before the next round / push reads it
-        if (recv_heads) GX_TRY(sync_counters(c));
+        // the host copy of the cursors shows the reservation as well (what bump_cursors_kernel does on the device)
+        if (recv_heads) { c->h_ctr->head_cursor += recv_heads; c->h_ctr->store_cursor += recv_store; }
     }
     m->pending.clear();   // every staged arena went through a round: the last one is in flight, the others are free again
     return GX_OK;
