@@ -1,9 +1,10 @@
 // gx_api.cu -- context, memory management and the C ABI of libgenomix_gb (include/genomix_gb.h).
 //
 // Host-side shape of one job (single GPU):
-//   gx_push_lines*  : per chunk   line index -> parse -> [grow table] -> extract+insert   (K1+K2)
-//   gx_finish       : heads -> slots, per-slot grouping/sort, size scan, serialise         (K3)
-//   gx_next_*       : stream the record bytes / Hyracks frames back to the caller
+//   gx_push_lines*  : per chunk   line index -> parse -> split by table region -> region upserts [grow on deferral]  (K1+K2)
+//   gx_push_records : serialised Nodes -> (key, mask, count) + heads -> upsert                                       (merge)
+//   gx_finish       : read-head groups, one-pass size scan + dense node list, record writer                          (K3)
+//   gx_next_*       : stream the record bytes / Hyracks frames back to the caller (serialised on demand when streaming)
 // which replaces the six-operator Hyracks job of JobGenBuildBrujinGraph.assignJob
 // (genomix-hyracks/.../graph/job/JobGenBuildBrujinGraph.java:79-90).
 #include <cuda_runtime.h>

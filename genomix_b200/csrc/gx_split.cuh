@@ -4,18 +4,19 @@
 // PreclusteredGroupWriter.java:76-136) with ONE radix pass on the top bits of the key hash instead of a comparison sort,
 // and the sender side of its M:N hash connector (MToNPartitioningMergingConnectorDescriptor.java:65-87) with the same pass:
 //
-//   split_count_kernel<KW>    read -> canonical k-mers -> histogram over buckets (owner GPU, table region). Exact record
-//                             counts per bucket, so that the placement pass writes a dense, gap-free record arena.
+//   split_count_kernel<KW>    read -> canonical k-mers -> histogram over buckets (owner GPU, table region), over every
+//                             16th line: the room each bucket gets in the record arena (estimate + slack; exact counts
+//                             for small chunks and for the rare chunk whose estimate a bucket overflows).
 //   split_place_kernel<KW>    read -> canonical k-mers + edge masks + read heads -> CTA-level multisplit in shared memory
-//                             -> bucket-sorted runs appended to the arena (or, for buckets owned by another GPU, straight
-//                             into that GPU's inbox over NVLink). No table access: a pure function of the text.
-//   upsert_regions_kernel<KW> persistent kernel that walks the arenas region by region, so that at any time all CTAs
-//                             upsert into the same few MB of the table (L2 hits instead of one HBM row activation per
-//                             k-mer occurrence), prefetching the next region into L2 as it goes.
+//                             -> bucket-sorted runs appended to each bucket's room. No table access: a pure function of
+//                             the text.
+//   upsert_regions_kernel<KW> persistent warps walk the arenas region by region (work items dealt by ticket), so that at
+//                             any time all warps upsert into the same few MB of the table: L2 hits instead of one HBM
+//                             row activation per k-mer occurrence.
 //
 // A random 16-byte table access that misses L2 costs a whole 128-byte line and a DRAM row activation (15.6 G upserts/s on
 // B200, profiles/r01_microbench_random_access.txt); the same access L2-resident runs 4x faster. Sorting the records by
-// region first costs one coalesced write + read of (8*KW + 2) bytes per occurrence plus a second extraction pass.
+// region first costs one coalesced write + read of (8*KW + 2) bytes per occurrence and 1/16 of a second extraction pass.
 #pragma once
 #include "gx_build.cuh"
 

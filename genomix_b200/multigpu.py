@@ -1,5 +1,5 @@
 """Host-side plumbing for the multi-GPU graph build: one process per GPU, reads sharded by byte range,
-k-mers hash-partitioned to their owner GPU inside libgenomix_gb (NCCL all-to-all-v). torch.distributed is used
+k-mers hash-partitioned to their owner GPU inside libgenomix_gb (all-to-all-v over NVLink; NCCL for the collectives). torch.distributed is used
 only to bootstrap (broadcast of the NCCL unique id) -- any backend works for that, gloo included.
 
 Reference counterpart: the partition layout of JobGen (genomix-hyracks/.../graph/job/JobGen.java:61-79: one

@@ -201,15 +201,19 @@ int gx_coverage_cutoff(gx_ctx* ctx, int32_t iterations, int64_t* cutoff, double*
  * One process per GPU. Bootstrap: rank 0 calls gx_mg_unique_id, the host side broadcasts the 128
  * bytes (torch.distributed / MPI / Hyracks RPC), every rank calls gx_mg_init. After the last
  * gx_push_*, every rank calls gx_mg_exchange (collective): staged k-mer and read-head records are
- * routed to owner = mix(key) mod n_ranks with an NCCL all-to-all-v over NVLink and inserted. */
+ * routed to owner = floor(mix(key) * n_ranks / 2^64) with an all-to-all-v over NVLink (copy-engine pushes into CUDA-IPC
+ * inboxes; GENOMIX_GB_NO_IPC=1: grouped ncclSend/ncclRecv) and upserted. The call is pipelined: the transfer of the last
+ * staged chunk is started but its records are upserted by the next gx_mg_exchange or by gx_finish, so with one exchange per
+ * pushed chunk the transfer runs under the next chunk's split. */
 int gx_mg_unique_id(uint8_t out_id[128]);
 int gx_mg_init(gx_ctx* ctx, const uint8_t id[128]);
 int gx_mg_exchange(gx_ctx* ctx);
 
 /* ---- timing hooks (device-side, CUDA events on the ctx's stream) ------------------------------ */
 /* Milliseconds spent by the ctx's kernels since gx_reset/gx_create, by phase:
- * [0] line index + parse, [1] extract + insert, [2] exchange (whole), [3] finish (heads + emit), [4] h2d copies,
- * [5] exchange: NCCL traffic on the communication stream, [6] exchange: upserts of received records. */
+ * [0] line index + parse, [1] region upserts (single GPU), [2] exchange (whole call, upserts included), [3] finish (heads + emit),
+ * [4] h2d copies, [5] exchange: NVLink pushes + arrival barrier on the communication stream (overlaps the next chunk's split),
+ * [6] exchange: upserts of own + received records, [7] split (bucket sizes + placement). */
 int gx_phase_ms(gx_ctx* ctx, float out_ms[8]);
 /* Number of kernel launches issued by this ctx since creation. */
 uint64_t gx_kernel_launches(gx_ctx* ctx);
