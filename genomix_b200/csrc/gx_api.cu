@@ -100,6 +100,7 @@ struct gx_ctx {
     DevBuf text, text2, nl_pos, nl_pos2, desc, tile_sums;
     DevBuf ht_key, ht_count, ht_start, hgroup, hentry, hperm, hoff, bkey, big_list;   // read-head groups (gx_finish)
     DevBuf tile_state, records, rec_offsets, parts, dense, dense_h, big_tiles;
+    DevBuf sort_perm[2], sort_hist, sort_sizes, dense2, dense_h2;   // gx_config.sort_output
     // streaming delivery of the record stream (gx_config.reserved[2] bit 0)
     bool stream_records = false;
     size_t slice_bytes = 64ull << 20;
@@ -786,8 +787,8 @@ int gx_create(const gx_config* cfg, gx_ctx** out) {
         return fail(nullptr, GX_ERR_INVALID, "gx_create: abi_version %d != %d", cfg->abi_version, GX_ABI_VERSION);
     if (cfg->kmer_length < 1 || cfg->kmer_length > 32 * GX_MAX_KW)
         return fail(nullptr, GX_ERR_INVALID, "gx_create: kmer_length %d outside [1, %d]", cfg->kmer_length, 32 * GX_MAX_KW);
-    if (cfg->sort_output != 0)
-        return fail(nullptr, GX_ERR_INVALID, "gx_create: sort_output is not implemented (record order is not observable downstream)");
+    if (cfg->sort_output != 0 && cfg->sort_output != 1)
+        return fail(nullptr, GX_ERR_INVALID, "gx_create: sort_output must be 0 (table-slot order) or 1 (KmerPointable order)");
     if (cfg->n_ranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->n_ranks || cfg->n_ranks > SP_MAX_RANKS)
         return fail(nullptr, GX_ERR_INVALID, "gx_create: bad rank %d of %d (at most %d ranks)", cfg->rank, cfg->n_ranks, SP_MAX_RANKS);
     int n_dev = 0;
@@ -876,7 +877,8 @@ void gx_destroy(gx_ctx* c) {
     for (auto e : c->event_pool) cudaEventDestroy(e);
     DevBuf* bufs[] = {&c->heads, &c->store, &c->text, &c->text2, &c->nl_pos, &c->nl_pos2, &c->desc, &c->tile_sums, &c->ht_key, &c->ht_count, &c->ht_start,
                       &c->hgroup, &c->hentry, &c->hperm, &c->hoff, &c->bkey, &c->big_list, &c->tile_state, &c->records, &c->rec_offsets,
-                      &c->parts, &c->dense, &c->dense_h, &c->big_tiles, &c->ring[0], &c->ring[1], &c->slice_idx,
+                      &c->parts, &c->dense, &c->dense_h, &c->big_tiles, &c->sort_perm[0], &c->sort_perm[1], &c->sort_hist, &c->sort_sizes,
+                      &c->dense2, &c->dense_h2, &c->ring[0], &c->ring[1], &c->slice_idx,
                       &c->tile_prefix, &c->deferred[0], &c->deferred[1], &c->region_new, &c->gstats,
                       &c->mrec, &c->moff, &c->mbase, &c->mkeys, &c->mmeta, &c->mcounts};
     for (auto* b : bufs) release(*b);
@@ -1170,6 +1172,47 @@ int gx_finish(gx_ctx* c) {
         return c->sticky = fail(c, GX_ERR_INVALID, "internal error: %llu occupied slots but %llu keys counted",
                                 (unsigned long long)c->n_nodes, (unsigned long long)distinct);
     a.n_nodes = c->n_nodes;
+    if (c->cfg.sort_output && c->n_nodes > 1) {
+        // KmerPointable order (gx_sort.cuh): LSD radix sort of the node indices over the key bytes, then the node list, the
+        // head-group references and the record offsets in the new order
+        if (c->n_nodes >= 0xffffffffull) return fail(c, GX_ERR_INVALID, "sort_output: more than 2^32-1 nodes on one rank");
+        const u64 n = c->n_nodes;
+        const u32 nb = (u32)(c->k + 3) / 4, n_tiles_s = (u32)((n + RS_TILE - 1) / RS_TILE);
+        const u64 s_tiles = (n + TS_TILE - 1) / TS_TILE;
+        GX_TRY(ensure(c, c->sort_perm[0], n * sizeof(u32)));
+        GX_TRY(ensure(c, c->sort_perm[1], n * sizeof(u32)));
+        GX_TRY(ensure(c, c->sort_hist, (size_t)256 * n_tiles_s * sizeof(u32)));
+        GX_TRY(ensure(c, c->dense2, (size_t)n * (c->kw + 1) * sizeof(u64)));
+        GX_TRY(ensure(c, c->dense_h2, (size_t)n * sizeof(u32)));
+        GX_TRY(ensure(c, c->sort_sizes, (size_t)n * sizeof(u32)));
+        GX_TRY(ensure(c, c->tile_sums, (s_tiles + 1) * sizeof(u64)));
+        ScopedPhase ph(c, PH_FINISH);
+        SortArgs sa{};
+        sa.dense = a.dense; sa.k = c->k; sa.n = n; sa.hist = (u32*)c->sort_hist.p; sa.n_tiles = n_tiles_s;
+        int cur = 0;
+        for (u32 byte = 0; byte < nb; ++byte) {
+            sa.perm_in = byte ? (const u32*)c->sort_perm[cur].p : nullptr;
+            sa.perm_out = (u32*)c->sort_perm[byte ? cur ^ 1 : 0].p;
+            sa.byte = byte;
+            c->ops->sort_pass(sa, c->stream);
+            GX_TRY(check_launch(c, "sort_pass"));
+            c->launches += 2;
+            if (byte) cur ^= 1;
+        }
+        c->ops->sort_gather(a.dense, a.dense_h, a.rec_offsets, (const u32*)c->sort_perm[cur].p, n, (u64*)c->dense2.p, (u32*)c->dense_h2.p,
+                            (u32*)c->sort_sizes.p, c->stream);
+        GX_TRY(check_launch(c, "sort_gather"));
+        tile_sum_u32_kernel<<<(unsigned)s_tiles, TS_THREADS, 0, c->stream>>>((const u32*)c->sort_sizes.p, n, (u64*)c->tile_sums.p);
+        GX_TRY(check_launch(c, "tile_sum_u32"));
+        scan_tile_sums_kernel<<<1, 1024, 0, c->stream>>>((u64*)c->tile_sums.p, s_tiles, &c->d_ctr->scratch[0]);
+        GX_TRY(check_launch(c, "scan_tile_sums"));
+        tile_scan_u32_to_u64_kernel<<<(unsigned)s_tiles, TS_THREADS, 0, c->stream>>>((const u32*)c->sort_sizes.p, n, (const u64*)c->tile_sums.p,
+                                                                                     a.rec_offsets);
+        GX_TRY(check_launch(c, "tile_scan_u32_to_u64"));
+        std::swap(c->dense, c->dense2);
+        std::swap(c->dense_h, c->dense_h2);
+        a.dense = (u64*)c->dense.p; a.dense_h = (u32*)c->dense_h.p;
+    }
     {
         // staging window per warp: 1.5x the average bytes of a tile of EW_NODES nodes; the rare tile that needs more is
         // written window by window

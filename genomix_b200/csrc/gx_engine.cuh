@@ -6,9 +6,11 @@
 //   gx_build.cuh   extraction helpers, insert_records (spills), init_table, rehash
 //   gx_emit.cuh    K3 read-head grouping, sizing, Node serialisation, graph statistics, Java partition hash
 //   gx_merge.cuh   serialised Node records back into (key, mask, count) + read heads (gx_push_records)
+//   gx_sort.cuh    optional KmerPointable order of the output (gx_config.sort_output)
 #pragma once
 #include "gx_emit.cuh"
 #include "gx_merge.cuh"
+#include "gx_sort.cuh"
 #include "gx_split.cuh"
 
 namespace gx {
@@ -35,6 +37,9 @@ struct EngineOps {
     void (*emit_write)(const EmitArgs& a, cudaStream_t st);
     void (*graph_stats)(const EmitArgs& a, GraphStatsDev* out, cudaStream_t st);
     void (*coverage_histogram)(const EmitArgs& a, u64* bins, u64 n_bins, cudaStream_t st);
+    void (*sort_pass)(const SortArgs& a, cudaStream_t st);   // histogram, scan, stable scatter of one key byte
+    void (*sort_gather)(const u64* dense, const u32* dense_h, const u64* rec_offsets, const u32* perm, u64 n, u64* dense_out,
+                        u32* dense_h_out, u32* sizes, cudaStream_t st);
     void (*merge_scan)(const MergeArgs& a, cudaStream_t st);
     void (*merge_apply)(const MergeArgs& a, cudaStream_t st);
     void (*route_heads)(const HeadRouteArgs& a, cudaStream_t st);

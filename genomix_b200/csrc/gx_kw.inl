@@ -63,6 +63,16 @@ void l_coverage_histogram(const EmitArgs& a, u64* bins, u64 n_bins, cudaStream_t
     if (a.n_nodes == 0) return;
     coverage_histogram_kernel<KW><<<grid_for(a.n_nodes, 256, 148 * 4), 256, 0, st>>>(a, bins, n_bins);
 }
+void l_sort_pass(const SortArgs& a, cudaStream_t st) {
+    const unsigned grid = (a.n_tiles + RS_WARPS - 1) / RS_WARPS;
+    sort_hist_kernel<KW><<<grid, RS_WARPS * 32, 0, st>>>(a);
+    sort_scan_kernel<<<1, 1024, 0, st>>>(a.hist, (u64)256 * a.n_tiles);
+    sort_scatter_kernel<KW><<<grid, RS_WARPS * 32, 0, st>>>(a);
+}
+void l_sort_gather(const u64* dense, const u32* dense_h, const u64* rec_offsets, const u32* perm, u64 n, u64* dense_out, u32* dense_h_out,
+                   u32* sizes, cudaStream_t st) {
+    sort_gather_kernel<KW><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dense, dense_h, rec_offsets, perm, n, dense_out, dense_h_out, sizes);
+}
 void l_merge_scan(const MergeArgs& a, cudaStream_t st) {
     if (a.n_rec) merge_scan_kernel<KW><<<(unsigned)((a.n_rec + 255) / 256), 256, 0, st>>>(a);
 }
@@ -106,6 +116,8 @@ const EngineOps OPS = {KW,
                        l_emit_write,
                        l_graph_stats,
                        l_coverage_histogram,
+                       l_sort_pass,
+                       l_sort_gather,
                        l_merge_scan,
                        l_merge_apply,
                        l_route_heads,

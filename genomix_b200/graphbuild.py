@@ -28,11 +28,13 @@ class GenomixError(RuntimeError):
 class GraphBuilder:
     def __init__(self, kmer_length: int, device: int = 0, rank: int = 0, n_ranks: int = 1,
                  expected_kmers: int = 0, chunk_bytes: int = 0, min_capacity: int = 0,
-                 start_small: bool = False, table_regions: int = 0, stream_records: bool = False):
+                 start_small: bool = False, table_regions: int = 0, stream_records: bool = False,
+                 sort_output: bool = False):
         """expected_kmers: optional hint (distinct k-mers this rank will own); chunk_bytes: internal chunk size;
         min_capacity / start_small: smallest table and "no sizing heuristics" (tests of the growth path);
         table_regions: regions of the region-sorted build (0 = sized for L2); stream_records: records are serialised on
-        demand while they are copied to the host (no device-resident record stream)."""
+        demand while they are copied to the host (no device-resident record stream); sort_output: records in KmerPointable
+        order, like the reference's part files (default: table-slot order)."""
         self._lib = _lib.load()
         cfg = GxConfig()
         cfg.abi_version = _lib.GX_ABI_VERSION
@@ -41,6 +43,7 @@ class GraphBuilder:
         cfg.rank = rank
         cfg.n_ranks = n_ranks
         cfg.expected_kmers = expected_kmers
+        cfg.sort_output = 1 if sort_output else 0
         cfg.reserved[0] = chunk_bytes or int(os.environ.get("GENOMIX_GB_CHUNK", "0"))
         cfg.reserved[1] = min_capacity
         cfg.reserved[2] = (256 if start_small else 0) | (1 if stream_records else 0)

@@ -60,9 +60,10 @@ typedef struct gx_config {
     int32_t device;             /* CUDA device ordinal */
     int32_t rank;               /* this process's partition index, 0 <= rank < n_ranks */
     int32_t n_ranks;            /* number of GPUs sharing the key space (1 = single GPU) */
-    int32_t sort_output;        /* must be 0: records leave in table-slot order. (The reference writes each part file in
-                                 * KmerPointable order, KmerPointable.java:94-107, but the Pregelix loader re-sorts, so the order
-                                 * is not observable downstream; a sorted stream is not implemented -> GX_ERR_INVALID.) */
+    int32_t sort_output;        /* 0: records leave in table-slot order (default: nothing downstream depends on the order, the
+                                 * Pregelix loader hashes vertices by key). 1: in KmerPointable order (KmerPointable.java:94-107:
+                                 * unsigned byte order of the Kmer bytes) like the reference's part files, which come out of a
+                                 * pre-clustered group-by over ExternalSortOperatorDescriptor; costs a radix sort of the nodes. */
     uint64_t expected_kmers;    /* hint: distinct canonical k-mers this rank will own (0 = grow on demand) */
     uint64_t reserved[4];       /* tuning/test knobs, 0 = default: [0] internal chunk bytes (256 MiB), [1] smallest table
                                  * capacity in slots (2^20), [2] bit 0: stream the records -- gx_finish sizes them, gx_next_records

@@ -553,3 +553,32 @@ def test_push_lines_device_cuts_chunks_at_line_ends():
                 gb.finish()
                 assert gb.stats()["lines"] == 3000
                 assert gx.types.canonical_records(gb.records()) == want
+
+
+@pytest.mark.parametrize("k,paired", [(3, False), (21, True), (31, False), (55, True), (91, False)])
+def test_sort_output_is_kmer_pointable_order(k, paired):
+    """gx_config.sort_output: the records leave in the order of KmerPointable.compare (KmerPointable.java:94-107: unsigned
+    byte order of the Kmer bytes), the order of the reference's part files; same record set, streamed or resident."""
+    gx = _gx()
+    rng = np.random.default_rng(500 + k)
+    text = random_reads_text(rng, 1500, k + 2, k + 70, paired=paired, genome_len=6000)
+    want = oracle_canonical_c(k, text) if k > 3 else oracle_canonical(k, text)
+    for kw in ({}, {"stream_records": True}):
+        with gx.GraphBuilder(k, sort_output=True, **kw) as gb:
+            gb.push_lines(text)
+            gb.finish()
+            stream = gb.records()
+            keys = [key[4:] for key, _ in gx.types.iter_records(stream)]        # Kmer bytes behind the VKmer length header
+            assert keys == sorted(keys) and len(set(keys)) == len(keys) == len(want)
+            assert gx.types.canonical_records(stream) == want
+            if not kw:
+                tuples = []
+                for frame in gb.iter_frames(16384):
+                    n = int.from_bytes(frame[-4:], "big")
+                    ends = [int.from_bytes(frame[len(frame) - 4 * (i + 2): len(frame) - 4 * (i + 1)], "big") for i in range(n)]
+                    start = 0
+                    for e in ends:
+                        nbk = int.from_bytes(frame[start:start + 4], "big")
+                        tuples.append(bytes(frame[start + 8:start + 8 + nbk]))
+                        start = e
+                assert tuples == keys                                            # frames carry the same order
