@@ -21,6 +21,16 @@ for k, paired in ((21, False), (55, True), (91, False)):
             assert got == want, (k, kw)
             gb.graph_statistics(); gb.coverage_histogram(); gb.coverage_cutoff()
             list(gb.iter_frames(65536))
+    with gx.GraphBuilder(k, sort_output=True) as gb:             # radix sort of the node list
+        gb.push_lines(text)
+        gb.finish()
+        assert gx.types.canonical_records(gb.records()) == want
+    import torch
+    dev = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda()
+    with gx.GraphBuilder(k, chunk_bytes=30000) as gb:             # chunk ends found on the device
+        gb.push_lines_device(dev.data_ptr(), dev.numel())
+        gb.finish()
+        assert gx.types.canonical_records(gb.records()) == want
     a = gx.build_graph(k, text)
     with gx.GraphBuilder(k) as gb:
         gb.push_records(a)
